@@ -1,0 +1,177 @@
+/*
+ * bpmf_b200.h -- C-ABI of libbpmf_b200.so, the B200 (sm_100a) drop-in for the native hot path of
+ * ebeauce/Seismic_BPMF.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Three groups of entry points, each citing the reference interface it replaces
+ * (paths relative to the reference tree):
+ *
+ *  (1) The symbols of BPMF/lib/libc.so that BPMF/clib.py binds (clib.py:26-84, libc.h:1-11,
+ *      libc.c:11,55,225,389,413,421,441,488,502,516).  Same names, same signatures, same
+ *      ownership rules (caller-allocated numpy buffers, void return, input of
+ *      time_dependent_threshold is mutated) -- so `clib.py` works unchanged when this library is
+ *      installed as BPMF/lib/libc.so.  Work runs on the current CUDA device.
+ *  (2) The native entry points behind `fast_matched_filter.matched_filter`
+ *      (BPMF/similarity_search.py:526-533, BPMF/dataset.py:4818-4827) and
+ *      `beampower.beampower.beamform` (BPMF/template_search.py:549-569).  Those two packages are
+ *      un-vendored pip dependencies of the reference (pyproject.toml:28-29); their C symbol names
+ *      are reproduced from the upstream projects as best known ([UPSTREAM-UNVERIFIED], SURVEY.md
+ *      Appendix A) next to explicit `bpmf_*` entry points.
+ *  (3) `caract_GPU` (BPMF/GPU.cu:7-24).
+ *
+ * Every `bpmf_*` function returns 0 on success or a negative BPMF_E_* code; the message is
+ * available from bpmf_last_error() (thread-local).  There is NO CPU fallback: without a usable
+ * CUDA device every compute entry point fails with BPMF_E_CUDA.
+ */
+#ifndef BPMF_B200_H
+#define BPMF_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPMF_OK 0
+#define BPMF_E_CUDA (-1)     /* CUDA runtime error / no device */
+#define BPMF_E_ARG (-2)      /* invalid argument / unsupported shape */
+#define BPMF_E_NOMEM (-3)    /* host or device allocation failed */
+
+/* matched-filter arithmetic selector */
+#define BPMF_MF_AUTO 0       /* tensor path when the shape allows it, else fp32 */
+#define BPMF_MF_FP32 1       /* direct form on FP32 CUDA cores (exact-grade, ~1e-6) */
+#define BPMF_MF_TC_FP16 2    /* tcgen05, fp16 operands (power-of-two pre-scaled), fp32 accumulate */
+#define BPMF_MF_TC_FP16X3 3  /* tcgen05, hi/lo split of both operands (3 MMAs), fp32-grade */
+
+const char *bpmf_last_error(void);
+int bpmf_device_count(void);
+/* library build id, e.g. "bpmf_b200 r1 sm_100a" */
+const char *bpmf_version(void);
+/* number of kernel launches issued by this library since process start (all threads) */
+unsigned long long bpmf_launch_count(void);
+
+/* ---------------------------------------------------------------- (3) BPMF/GPU.cu:7-24 */
+void caract_GPU(void);
+
+/* ---------------------------------------------------------------- (2a) matched filter
+ * cc_sum[t, n] = sum_{s,c: w!=0} w[t,s,c] * CC(templates[t,s,c,:], data[s,c, n*step+moveouts[t,s,c] : +L])
+ * Layouts (C order): templates (T,S,C,L) f32; moveouts (T,S,C) i32 (may be negative);
+ * weights (T,S,C) f32; data (S,C,N) f32; n_corr = (N-L)/step + 1.
+ * normalize: 0 "short" (no window-mean removal), 1 "full".
+ * network_sum: 1 -> out (T, n_corr); 0 -> out (T, n_corr, S, C) unweighted per-channel CC.
+ */
+size_t bpmf_mf_n_corr(size_t n_samples_data, size_t n_samples_template, size_t step);
+
+/* Host-pointer entry point (what a ctypes/cffi binding calls).  Copies in, runs on the current
+ * device, copies out; templates are processed in chunks sized to the free device memory. */
+int bpmf_matched_filter(const float *templates, const int *moveouts, const float *weights,
+                        const float *data, size_t step, size_t n_samples_template,
+                        size_t n_samples_data, size_t n_templates, size_t n_stations,
+                        size_t n_components, int normalize, int network_sum, int precision,
+                        float *cc_out);
+
+/* Device-pointer entry point: every pointer is device memory, work is enqueued on `stream`
+ * (a cudaStream_t passed as void*), no host synchronisation.  `workspace` must hold at least
+ * bpmf_mf_workspace_bytes(...) bytes.  cc_pitch = elements between consecutive template rows of
+ * d_cc (>= n_corr; ignored when network_sum == 0). */
+size_t bpmf_mf_workspace_bytes(size_t n_samples_template, size_t n_samples_data,
+                               size_t n_templates, size_t n_stations, size_t n_components,
+                               size_t step, int normalize, int network_sum, int precision);
+int bpmf_matched_filter_dev(const float *d_templates, const int *d_moveouts,
+                            const float *d_weights, const float *d_data, size_t step,
+                            size_t n_samples_template, size_t n_samples_data, size_t n_templates,
+                            size_t n_stations, size_t n_components, int normalize,
+                            int network_sum, int precision, void *d_workspace,
+                            size_t workspace_bytes, float *d_cc, size_t cc_pitch, void *stream);
+/* the arithmetic bpmf_matched_filter_dev resolves `precision` to for this shape */
+int bpmf_mf_resolve_precision(size_t n_samples_template, size_t step, int normalize,
+                              int network_sum, int precision);
+
+/* Upstream fast_matched_filter CPU/GPU symbol [UPSTREAM-UNVERIFIED signature]: the function
+ * fast_matched_filter's own ctypes wrapper binds.  sum_square_templates is accepted and ignored
+ * (recomputed on the device). */
+void matched_filter(float *templates, float *sum_square_templates, int *moveouts, float *data,
+                    float *weights, size_t step, size_t n_samples_template, size_t n_samples_data,
+                    size_t n_templates, size_t n_stations, size_t n_components, size_t n_corr,
+                    int normalize, float *cc_sum);
+void matched_filter_no_sum(float *templates, float *sum_square_templates, int *moveouts,
+                           float *data, float *weights, size_t step, size_t n_samples_template,
+                           size_t n_samples_data, size_t n_templates, size_t n_stations,
+                           size_t n_components, size_t n_corr, int normalize, float *cc);
+
+/* ---------------------------------------------------------------- (2b) beamforming
+ * U[s,p,t] = sum_c weights_phases[s,c,p] * features[s,c,t]
+ * b[k,t]   = sum_s weights_sources[k,s] * sum_p U[s,p,t + moveouts[k,s,p]]
+ * Layouts: features (S,C,N) f32; moveouts (K,S,P) i32; weights_phases (S,C,P) f32;
+ * weights_sources (K,S) f32.  flexible: 0 "strict", 1 "flexible" (template_search.py:529-537).
+ * source_offset is added to every reported argmax (source-sharded callers).
+ */
+int bpmf_beamform_max(const float *features, const int *moveouts, const float *weights_phases,
+                      const float *weights_sources, size_t n_sources, size_t n_stations,
+                      size_t n_components, size_t n_phases, size_t n_samples, int flexible,
+                      int source_offset, float *maxbeam, int *maxbeam_sources);
+int bpmf_beamform_full(const float *features, const int *moveouts, const float *weights_phases,
+                       const float *weights_sources, size_t n_sources, size_t n_stations,
+                       size_t n_components, size_t n_phases, size_t n_samples, int flexible,
+                       float *beam);
+size_t bpmf_beam_workspace_bytes(size_t n_sources, size_t n_stations, size_t n_components,
+                                 size_t n_phases, size_t n_samples);
+/* device-pointer variants, enqueued on `stream`, no host synchronisation */
+int bpmf_beamform_max_dev(const float *d_features, const int *d_moveouts,
+                          const float *d_weights_phases, const float *d_weights_sources,
+                          size_t n_sources, size_t n_stations, size_t n_components,
+                          size_t n_phases, size_t n_samples, int flexible, int source_offset,
+                          void *d_workspace, size_t workspace_bytes, float *d_maxbeam,
+                          int *d_maxbeam_sources, void *stream);
+int bpmf_beamform_full_dev(const float *d_features, const int *d_moveouts,
+                           const float *d_weights_phases, const float *d_weights_sources,
+                           size_t n_sources, size_t n_stations, size_t n_components,
+                           size_t n_phases, size_t n_samples, int flexible, void *d_workspace,
+                           size_t workspace_bytes, float *d_beam, void *stream);
+/* merge per-shard (max, argmax) pairs: in-place  a = better(a, b), ties -> lower source index */
+int bpmf_beam_merge_dev(float *d_max_a, int *d_arg_a, const float *d_max_b, const int *d_arg_b,
+                        size_t n_samples, void *stream);
+
+/* ---------------------------------------------------------------- (1) BPMF/lib/libc.so symbols */
+/* libc.c:11-16   ; clib.py:26-33 */
+void kurtosis(float *signal, int W, int n_stations, int n_components, int length, float *kurto);
+/* libc.c:55-68   ; clib.py:35-49 */
+void find_similar_moveouts(float *moveouts, float *source_longitude, float *source_latitude,
+                           float *cell_longitude, float *cell_latitude, float threshold,
+                           size_t n_sources, size_t n_stations, size_t n_cells_longitude,
+                           size_t n_cells_latitude, size_t n_stations_for_diff, int num_threads,
+                           int *redundant_sources);
+/* libc.c:225-238 ; clib.py:51-65 */
+void find_similar_moveouts2(float *moveouts, float *source_longitude, float *source_latitude,
+                            float *cell_longitude, float *cell_latitude, float threshold,
+                            size_t n_sources, size_t n_stations, size_t n_cells_longitude,
+                            size_t n_cells_latitude, size_t n_stations_for_diff, int num_threads,
+                            int *redundant_sources);
+/* libc.c:441-445 ; clib.py:67-73 */
+void select_cc_indexes(float *cc, float *threshold, size_t search_win, size_t n_corr,
+                       int *selection);
+/* libc.c:516-524 ; clib.py:75-84.  time_series is overwritten (zeros replaced), like libc.c:610 */
+void time_dependent_threshold(float *time_series, float *gaussian_sample, float num_dev,
+                              size_t num_samples, size_t half_window_samp, size_t shift_samp,
+                              int num_threads, float *threshold);
+/* helper symbols the reference library also exports (libc.h:5-10); tiny host utilities */
+void swap(float *xp, float *yp);
+void selectionSort(float *arr, int n);
+void sort_indexes(const float *moveouts, size_t *sorted_indexes, size_t n_stations);
+float _compute_average(float *x, size_t len_x);
+float _compute_std(float *x, float x_mean, size_t len_x);
+
+/* device-resident batch form of time_dependent_threshold: B series of n samples each (row pitch
+ * `pitch` elements), e.g. the (T, n_corr) CC slab straight after bpmf_matched_filter_dev, so the
+ * CC never leaves the GPU before thresholding.  Series are modified in place. */
+size_t bpmf_threshold_workspace_bytes(size_t n_series, size_t num_samples, size_t half_window_samp,
+                                      size_t shift_samp);
+int bpmf_time_dependent_threshold_dev(float *d_series, size_t pitch, size_t n_series,
+                                      const float *d_gaussian_sample, float num_dev,
+                                      size_t num_samples, size_t half_window_samp,
+                                      size_t shift_samp, void *d_workspace, size_t workspace_bytes,
+                                      float *d_threshold, size_t threshold_pitch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPMF_B200_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of libbpmf_b200.so (the C-ABI declared in include/bpmf_b200.h).
+
+There is no CPU fallback: if the shared object is missing the import of any compute module raises,
+and every compute entry point raises :class:`BpmfError` when the library reports a failure
+(no CUDA device, bad shapes, out of memory).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libbpmf_b200.so")
+
+OK = 0
+MF_AUTO, MF_FP32, MF_TC_FP16, MF_TC_FP16X3 = 0, 1, 2, 3
+PRECISIONS = {"auto": MF_AUTO, "fp32": MF_FP32, "fp16": MF_TC_FP16, "tc": MF_TC_FP16,
+              "fp16x3": MF_TC_FP16X3, "tc3": MF_TC_FP16X3}
+
+
+class BpmfError(RuntimeError):
+    pass
+
+
+fp = C.POINTER(C.c_float)
+ip = C.POINTER(C.c_int)
+z = C.c_size_t
+vp = C.c_void_p
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "bpmf_last_error": (C.c_char_p, []),
+    "bpmf_version": (C.c_char_p, []),
+    "bpmf_device_count": (C.c_int, []),
+    "bpmf_launch_count": (C.c_ulonglong, []),
+    "caract_GPU": (None, []),
+    "bpmf_mf_n_corr": (z, [z, z, z]),
+    "bpmf_matched_filter": (C.c_int, [fp, ip, fp, fp, z, z, z, z, z, z, C.c_int, C.c_int, C.c_int, fp]),
+    "bpmf_mf_workspace_bytes": (z, [z, z, z, z, z, z, C.c_int, C.c_int, C.c_int]),
+    "bpmf_matched_filter_dev": (C.c_int, [vp, vp, vp, vp, z, z, z, z, z, z, C.c_int, C.c_int, C.c_int,
+                                          vp, z, vp, z, vp]),
+    "bpmf_mf_resolve_precision": (C.c_int, [z, z, C.c_int, C.c_int, C.c_int]),
+    "matched_filter": (None, [fp, fp, ip, fp, fp, z, z, z, z, z, z, z, C.c_int, fp]),
+    "matched_filter_no_sum": (None, [fp, fp, ip, fp, fp, z, z, z, z, z, z, z, C.c_int, fp]),
+    "bpmf_beamform_max": (C.c_int, [fp, ip, fp, fp, z, z, z, z, z, C.c_int, C.c_int, fp, ip]),
+    "bpmf_beamform_full": (C.c_int, [fp, ip, fp, fp, z, z, z, z, z, C.c_int, fp]),
+    "bpmf_beam_workspace_bytes": (z, [z, z, z, z, z]),
+    "bpmf_beamform_max_dev": (C.c_int, [vp, vp, vp, vp, z, z, z, z, z, C.c_int, C.c_int, vp, z, vp, vp, vp]),
+    "bpmf_beamform_full_dev": (C.c_int, [vp, vp, vp, vp, z, z, z, z, z, C.c_int, vp, z, vp, vp]),
+    "bpmf_beam_merge_dev": (C.c_int, [vp, vp, vp, vp, z, vp]),
+    "kurtosis": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
+    "find_similar_moveouts": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),
+    "find_similar_moveouts2": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),
+    "select_cc_indexes": (None, [fp, fp, z, z, ip]),
+    "time_dependent_threshold": (None, [fp, fp, C.c_float, z, z, z, C.c_int, fp]),
+    "swap": (None, [fp, fp]),
+    "selectionSort": (None, [fp, C.c_int]),
+    "sort_indexes": (None, [fp, C.POINTER(z), z]),
+    "_compute_average": (C.c_float, [fp, z]),
+    "_compute_std": (C.c_float, [fp, C.c_float, z]),
+    "bpmf_threshold_workspace_bytes": (z, [z, z, z, z]),
+    "bpmf_time_dependent_threshold_dev": (C.c_int, [vp, z, z, vp, C.c_float, z, z, z, vp, z, vp, z, vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BpmfError(
+            "libbpmf_b200.so not found at %s -- build it with `python -m seismic_bpmf_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != OK:
+        msg = load().bpmf_last_error()
+        raise BpmfError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def require_device():
+    n = load().bpmf_device_count()
+    if n <= 0:
+        raise BpmfError("no CUDA device is visible: seismic_bpmf_b200 has no CPU fallback")
+    return n

@@ -1,0 +1,373 @@
+// beam.cu -- shift-and-stack network response (beamforming / backprojection).
+//
+// Replaces the native kernels behind beampower.beampower.beamform as BPMF calls it
+// (BPMF/template_search.py:549-569; math in tutorial 5_backprojection.ipynb:876-882,928-929);
+// semantics: SURVEY.md A.2.
+//
+//   prestack : U[s,p,t] = sum_c weights_phases[s,c,p] * features[s,c,t]        (HBM-bound)
+//   beam     : b[k,t]   = sum_{s,p} weights_sources[k,s] * U[s,p,t + tau[k,s,p]]
+//              CTA = 2048-sample time tile x a chunk of sources, processed 8 sources at a time
+//              with 8x8 register accumulators per thread.  The (station, phase) loop is OUTER so
+//              only one row segment of U lives in shared memory at a time; every gather-FMA costs
+//              one conflict-free 4-byte LDS (lanes = consecutive samples).  Roofline: shared-memory
+//              bandwidth, 128 B/clk/SM = 32 gather-FMA/clk/SM.
+//   reduce   : "max" keeps a running (max, argmax) per sample in registers and merges source
+//              chunks with a packed 64-bit atomicMax (value-ordered bits << 32 | ~k, so ties go to
+//              the lowest source index); "none" stores b[k,t].
+#include "common.cuh"
+
+namespace bpmf {
+
+constexpr int B_THREADS = 256;
+constexpr int B_R = 8;                    // samples per thread
+constexpr int B_TT = B_THREADS * B_R;     // 2048-sample tile
+constexpr int B_KB = 8;                   // sources per register block
+constexpr int B_CAP = B_TT + 1024;        // staged row segment (floats)
+
+__global__ void beam_prestack_kernel(const float *__restrict__ features,
+                                     const float *__restrict__ wp, int C, int P, size_t N,
+                                     float *__restrict__ U) {
+    const int sp = blockIdx.y;  // s * P + p
+    const int s = sp / P, p = sp % P;
+    const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (t >= N) return;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int n_here = (N - t >= 4) ? 4 : (int)(N - t);
+    for (int c = 0; c < C; c++) {
+        const float w = wp[((size_t)s * C + c) * P + p];
+        if (w == 0.f) continue;
+        const float *f = features + ((size_t)s * C + c) * N + t;
+        for (int i = 0; i < n_here; i++) a[i] = fmaf(w, f[i], a[i]);
+    }
+    float *u = U + (size_t)sp * N + t;
+    for (int i = 0; i < n_here; i++) u[i] = a[i];
+}
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// per-source valid time range for out_of_bounds="strict": [tlo, thi] inclusive
+__global__ void beam_source_bounds_kernel(const int *__restrict__ tau, const float *__restrict__ beta,
+                                          size_t K, int S, int P, long long N, int *__restrict__ tlo,
+                                          int *__restrict__ thi) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    long long mn = 0, mx = 0;
+    bool any = false;
+    for (int s = 0; s < S; s++) {
+        if (beta[k * S + s] == 0.f) continue;
+        for (int p = 0; p < P; p++) {
+            const long long m = tau[(k * S + s) * P + p];
+            if (!any) { mn = mx = m; any = true; }
+            mn = m < mn ? m : mn;
+            mx = m > mx ? m : mx;
+        }
+    }
+    long long lo = 0, hi = N - 1;
+    if (any) {
+        if (mn < 0) lo = -mn;
+        hi = N - 1 - mx;
+        if (hi > N - 1) hi = N - 1;
+    }
+    tlo[k] = (int)lo;
+    thi[k] = (int)(hi < -1 ? -1 : hi);
+}
+
+template <bool REDUCE_MAX>
+__global__ void __launch_bounds__(B_THREADS, 2)
+    beam_kernel(const float *__restrict__ U, const int *__restrict__ tau,
+                const float *__restrict__ beta, const int *__restrict__ tlo,
+                const int *__restrict__ thi, size_t K, int S, int P, long long N, int strict,
+                size_t k_chunk, unsigned long long *__restrict__ keys, float *__restrict__ beam) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *buf = reinterpret_cast<float *>(smem_raw);            // B_CAP
+    int *tau_s = reinterpret_cast<int *>(buf + B_CAP);           // B_KB * S * P
+    float *beta_s = reinterpret_cast<float *>(tau_s + B_KB * S * P);  // B_KB * S
+
+    const int tid = threadIdx.x;
+    const long long t0 = (long long)blockIdx.x * B_TT;
+    const size_t k_begin = (size_t)blockIdx.y * k_chunk;
+    const size_t k_end = (k_begin + k_chunk < K) ? k_begin + k_chunk : K;
+    const int SP = S * P;
+
+    float best[B_R];
+    unsigned bestk[B_R];
+#pragma unroll
+    for (int r = 0; r < B_R; r++) { best[r] = -INFINITY; bestk[r] = 0u; }
+
+    for (size_t kb = k_begin; kb < k_end; kb += B_KB) {
+        const int nk = (int)((k_end - kb < (size_t)B_KB) ? (k_end - kb) : (size_t)B_KB);
+        __syncthreads();
+        for (int i = tid; i < B_KB * SP; i += B_THREADS) {
+            const int kk = i / SP;
+            tau_s[i] = (kk < nk) ? tau[(kb + kk) * SP + (i - kk * SP)] : 0;
+        }
+        for (int i = tid; i < B_KB * S; i += B_THREADS) {
+            const int kk = i / S;
+            beta_s[i] = (kk < nk) ? beta[(kb + kk) * S + (i - kk * S)] : 0.f;
+        }
+        __syncthreads();
+
+        float acc[B_KB][B_R];
+#pragma unroll
+        for (int kk = 0; kk < B_KB; kk++)
+#pragma unroll
+            for (int r = 0; r < B_R; r++) acc[kk][r] = 0.f;
+
+        for (int sp = 0; sp < SP; sp++) {
+            const int s = sp / P;
+            const float *row = U + (size_t)sp * N;
+            long long wlo = 0;
+            bool staged = false;
+#pragma unroll
+            for (int kk = 0; kk < B_KB; kk++) {
+                const float b = beta_s[kk * S + s];
+                if (b == 0.f) continue;  // CTA-uniform
+                const long long tk = tau_s[kk * SP + sp];
+                if (!staged || tk < wlo || tk + B_TT > wlo + B_CAP) {
+                    __syncthreads();
+                    wlo = tk - (B_CAP - B_TT) / 4;  // keep most of the slack ahead of this source
+                    for (int i = tid; i < B_CAP; i += B_THREADS) {
+                        const long long g = t0 + wlo + i;
+                        buf[i] = (g >= 0 && g < N) ? __ldg(row + g) : 0.f;
+                    }
+                    staged = true;
+                    __syncthreads();
+                }
+                const float *src = buf + (int)(tk - wlo) + tid;
+#pragma unroll
+                for (int r = 0; r < B_R; r++) acc[kk][r] = fmaf(b, src[B_THREADS * r], acc[kk][r]);
+            }
+        }
+
+#pragma unroll
+        for (int kk = 0; kk < B_KB; kk++) {
+            if (kk < nk) {
+                const size_t k = kb + kk;
+                long long lo_k = 0, hi_k = N - 1;
+                if (strict) { lo_k = tlo[k]; hi_k = thi[k]; }
+#pragma unroll
+                for (int r = 0; r < B_R; r++) {
+                    const long long t = t0 + tid + B_THREADS * r;
+                    const float v = (t >= lo_k && t <= hi_k) ? acc[kk][r] : 0.f;
+                    if (REDUCE_MAX) {
+                        if (v > best[r]) { best[r] = v; bestk[r] = (unsigned)k; }
+                    } else if (t < N) {
+                        beam[k * (size_t)N + (size_t)t] = v;
+                    }
+                }
+            }
+        }
+    }
+    if (REDUCE_MAX && k_end > k_begin) {
+#pragma unroll
+        for (int r = 0; r < B_R; r++) {
+            const long long t = t0 + tid + B_THREADS * r;
+            if (t < N) {
+                const unsigned long long key =
+                    ((unsigned long long)ordered_bits(best[r]) << 32) | (unsigned long long)(~bestk[r]);
+                atomicMax(keys + t, key);
+            }
+        }
+    }
+}
+
+__global__ void beam_finalize_kernel(const unsigned long long *__restrict__ keys, size_t N,
+                                     int source_offset, float *__restrict__ maxbeam,
+                                     int *__restrict__ argmax) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const unsigned long long key = keys[t];
+    if (key == 0ull) {  // no source at all
+        maxbeam[t] = 0.f;
+        argmax[t] = source_offset;
+        return;
+    }
+    maxbeam[t] = from_ordered_bits((unsigned)(key >> 32));
+    argmax[t] = (int)(~(unsigned)(key & 0xffffffffull)) + source_offset;
+}
+
+__global__ void beam_merge_kernel(float *__restrict__ ma, int *__restrict__ aa,
+                                  const float *__restrict__ mb, const int *__restrict__ ab, size_t N) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const float va = ma[t], vb = mb[t];
+    const int ka = aa[t], kb = ab[t];
+    if (vb > va || (vb == va && kb < ka)) { ma[t] = vb; aa[t] = kb; }
+}
+
+static size_t beam_smem_bytes(size_t S, size_t P) {
+    return sizeof(float) * B_CAP + sizeof(int) * B_KB * S * P + sizeof(float) * B_KB * S;
+}
+
+struct BeamWs {
+    float *U;
+    int *tlo, *thi;
+    unsigned long long *keys;
+};
+
+static BeamWs carve(Workspace &ws, size_t K, size_t S, size_t P, size_t N) {
+    BeamWs b;
+    b.U = ws.take<float>(S * P * N);
+    b.tlo = ws.take<int>(K);
+    b.thi = ws.take<int>(K);
+    b.keys = ws.take<unsigned long long>(N);
+    return b;
+}
+
+static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, const float *d_wp,
+                    const float *d_beta, size_t K, size_t S, size_t C, size_t P, size_t N,
+                    int flexible, int source_offset, void *d_ws, size_t ws_bytes, float *d_max,
+                    int *d_arg, float *d_beam, cudaStream_t st) {
+    BPMF_REQUIRE(S > 0 && C > 0 && P > 0 && N > 0, "beamform: empty input");
+    BPMF_REQUIRE(N < (size_t)1 << 31 && K < (size_t)1 << 31, "beamform: size exceeds int32 indexing");
+    Workspace ws(d_ws, ws_bytes);
+    BeamWs b = carve(ws, K, S, P, N);
+    BPMF_REQUIRE(ws.ok(), "beamform: workspace too small (%zu < %zu)", ws_bytes, ws.used);
+    const size_t smem = beam_smem_bytes(S, P);
+    BPMF_REQUIRE(smem <= 200 * 1024, "beamform: too many stations x phases for one tile (%zu x %zu)", S, P);
+
+    {
+        dim3 grid((unsigned)((N + 1023) / 1024), (unsigned)(S * P));
+        beam_prestack_kernel<<<grid, 256, 0, st>>>(d_features, d_wp, (int)C, (int)P, N, b.U);
+        BPMF_LAUNCH_CHECK();
+    }
+    if (K > 0) {
+        beam_source_bounds_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(
+            d_tau, d_beta, K, (int)S, (int)P, (long long)N, b.tlo, b.thi);
+        BPMF_LAUNCH_CHECK();
+    }
+    const size_t n_tiles = (N + B_TT - 1) / B_TT;
+    if (reduce_max) {
+        BPMF_CUDA(cudaMemsetAsync(b.keys, 0, sizeof(unsigned long long) * N, st));
+        if (K > 0) {
+            // enough source chunks to fill the machine when the time axis is short
+            const size_t want = (size_t)num_sms() * 4;
+            size_t n_chunks = (n_tiles >= want) ? 1 : (want + n_tiles - 1) / n_tiles;
+            size_t k_chunk = align_up((K + n_chunks - 1) / n_chunks, B_KB);
+            n_chunks = (K + k_chunk - 1) / k_chunk;
+            BPMF_REQUIRE(n_chunks <= 65535, "beamform: too many source chunks");
+            BPMF_CUDA(cudaFuncSetAttribute(beam_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
+            beam_kernel<true><<<grid, B_THREADS, smem, st>>>(b.U, d_tau, d_beta, b.tlo, b.thi, K,
+                                                             (int)S, (int)P, (long long)N,
+                                                             flexible ? 0 : 1, k_chunk, b.keys, nullptr);
+            BPMF_LAUNCH_CHECK();
+        }
+        beam_finalize_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(b.keys, N, source_offset,
+                                                                         d_max, d_arg);
+        BPMF_LAUNCH_CHECK();
+    } else if (K > 0) {
+        size_t k_chunk = B_KB * 8;
+        size_t n_chunks = (K + k_chunk - 1) / k_chunk;
+        if (n_chunks > 65535) {
+            k_chunk = align_up((K + 65534) / 65535, B_KB);
+            n_chunks = (K + k_chunk - 1) / k_chunk;
+        }
+        BPMF_CUDA(cudaFuncSetAttribute(beam_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
+        beam_kernel<false><<<grid, B_THREADS, smem, st>>>(b.U, d_tau, d_beta, b.tlo, b.thi, K, (int)S,
+                                                          (int)P, (long long)N, flexible ? 0 : 1,
+                                                          k_chunk, nullptr, d_beam);
+        BPMF_LAUNCH_CHECK();
+    }
+    return BPMF_OK;
+}
+
+}  // namespace bpmf
+
+using namespace bpmf;
+
+extern "C" size_t bpmf_beam_workspace_bytes(size_t K, size_t S, size_t C, size_t P, size_t N) {
+    (void)C;
+    Workspace ws(nullptr, 0);
+    carve(ws, K, S, P, N);
+    return ws.used;
+}
+
+extern "C" int bpmf_beamform_max_dev(const float *d_features, const int *d_moveouts,
+                                     const float *d_weights_phases, const float *d_weights_sources,
+                                     size_t K, size_t S, size_t C, size_t P, size_t N, int flexible,
+                                     int source_offset, void *d_workspace, size_t workspace_bytes,
+                                     float *d_maxbeam, int *d_maxbeam_sources, void *stream) {
+    return beam_run(true, d_features, d_moveouts, d_weights_phases, d_weights_sources, K, S, C, P, N,
+                    flexible, source_offset, d_workspace, workspace_bytes, d_maxbeam,
+                    d_maxbeam_sources, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int bpmf_beamform_full_dev(const float *d_features, const int *d_moveouts,
+                                      const float *d_weights_phases, const float *d_weights_sources,
+                                      size_t K, size_t S, size_t C, size_t P, size_t N, int flexible,
+                                      void *d_workspace, size_t workspace_bytes, float *d_beam,
+                                      void *stream) {
+    return beam_run(false, d_features, d_moveouts, d_weights_phases, d_weights_sources, K, S, C, P, N,
+                    flexible, 0, d_workspace, workspace_bytes, nullptr, nullptr, d_beam,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int bpmf_beam_merge_dev(float *d_max_a, int *d_arg_a, const float *d_max_b,
+                                   const int *d_arg_b, size_t n_samples, void *stream) {
+    if (n_samples == 0) return BPMF_OK;
+    beam_merge_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_max_a, d_arg_a, d_max_b, d_arg_b, n_samples);
+    BPMF_LAUNCH_CHECK();
+    return BPMF_OK;
+}
+
+static int beam_host(bool reduce_max, const float *features, const int *moveouts, const float *wp,
+                     const float *beta, size_t K, size_t S, size_t C, size_t P, size_t N, int flexible,
+                     int source_offset, float *maxbeam, int *arg, float *beam) {
+    DevBuf f, tau, dwp, dbeta, ws, o1, o2;
+    BPMF_CUDA(f.alloc(sizeof(float) * S * C * N));
+    BPMF_CUDA(tau.alloc(sizeof(int) * K * S * P));
+    BPMF_CUDA(dwp.alloc(sizeof(float) * S * C * P));
+    BPMF_CUDA(dbeta.alloc(sizeof(float) * K * S));
+    const size_t wsb = bpmf_beam_workspace_bytes(K, S, C, P, N);
+    BPMF_CUDA(ws.alloc(wsb));
+    cudaStream_t st = nullptr;
+    BPMF_CUDA(cudaMemcpyAsync(f.p, features, sizeof(float) * S * C * N, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(tau.p, moveouts, sizeof(int) * K * S * P, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(dwp.p, wp, sizeof(float) * S * C * P, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(dbeta.p, beta, sizeof(float) * K * S, cudaMemcpyHostToDevice, st));
+    int rc;
+    if (reduce_max) {
+        BPMF_CUDA(o1.alloc(sizeof(float) * N));
+        BPMF_CUDA(o2.alloc(sizeof(int) * N));
+        rc = bpmf_beamform_max_dev(f.as<float>(), tau.as<int>(), dwp.as<float>(), dbeta.as<float>(), K,
+                                   S, C, P, N, flexible, source_offset, ws.p, wsb, o1.as<float>(),
+                                   o2.as<int>(), st);
+        if (rc != BPMF_OK) return rc;
+        BPMF_CUDA(cudaMemcpyAsync(maxbeam, o1.p, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+        BPMF_CUDA(cudaMemcpyAsync(arg, o2.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    } else {
+        BPMF_CUDA(o1.alloc(sizeof(float) * K * N));
+        rc = bpmf_beamform_full_dev(f.as<float>(), tau.as<int>(), dwp.as<float>(), dbeta.as<float>(), K,
+                                    S, C, P, N, flexible, ws.p, wsb, o1.as<float>(), st);
+        if (rc != BPMF_OK) return rc;
+        BPMF_CUDA(cudaMemcpyAsync(beam, o1.p, sizeof(float) * K * N, cudaMemcpyDeviceToHost, st));
+    }
+    BPMF_CUDA(cudaStreamSynchronize(st));
+    return BPMF_OK;
+}
+
+extern "C" int bpmf_beamform_max(const float *features, const int *moveouts,
+                                 const float *weights_phases, const float *weights_sources, size_t K,
+                                 size_t S, size_t C, size_t P, size_t N, int flexible,
+                                 int source_offset, float *maxbeam, int *maxbeam_sources) {
+    return beam_host(true, features, moveouts, weights_phases, weights_sources, K, S, C, P, N, flexible,
+                     source_offset, maxbeam, maxbeam_sources, nullptr);
+}
+
+extern "C" int bpmf_beamform_full(const float *features, const int *moveouts,
+                                  const float *weights_phases, const float *weights_sources, size_t K,
+                                  size_t S, size_t C, size_t P, size_t N, int flexible, float *beam) {
+    return beam_host(false, features, moveouts, weights_phases, weights_sources, K, S, C, P, N, flexible,
+                     0, nullptr, nullptr, beam);
+}

@@ -1,0 +1,182 @@
+// mf_prepass.cu -- matched-filter pre-pass kernels shared by the fp32 and tensor paths:
+//   * per-(template, channel) sum of squares / sum           (fast_matched_filter computes
+//     sum_square_templates on the host before its native call [UPSTREAM-UNVERIFIED])
+//   * per-template valid output range from weights + moveouts
+//   * per-channel sliding window energy  E[ch][j] = sum_{k<L} d[ch][j+k]^2, j in [0, N-L]
+//     accumulated in float64 block-local prefix sums (SURVEY section 7 "Sliding energy in FP32").
+// All HBM-bound streaming kernels: reads 4*S*C*N, writes 4*S*C*(N-L+1) (x2 for normalize=full).
+#include "common.cuh"
+
+namespace bpmf {
+
+// ---------------------------------------------------------------- template statistics
+__global__ void mf_template_stats_kernel(const float *__restrict__ templates, size_t n_rows,
+                                         size_t L, float *__restrict__ sst,
+                                         float *__restrict__ sumt) {
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const float *p = templates + row * L;
+    double a = 0.0, b = 0.0;
+    for (size_t k = lane; k < L; k += 32) {
+        const double v = (double)p[k];
+        a += v * v;
+        b += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        sst[row] = (float)a;
+        sumt[row] = (float)b;
+    }
+}
+
+// ---------------------------------------------------------------- per-template output bounds
+__global__ void mf_bounds_kernel(const int *__restrict__ moveouts, const float *__restrict__ weights,
+                                 size_t T, size_t SC, long long N, long long L, long long step,
+                                 long long n_corr, int *__restrict__ lo, int *__restrict__ hi) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    long long mn = 0, mx = 0;
+    bool any = false;
+    for (size_t ch = 0; ch < SC; ch++) {
+        if (weights[t * SC + ch] == 0.f) continue;
+        const long long m = moveouts[t * SC + ch];
+        if (!any) { mn = mx = m; any = true; }
+        mn = m < mn ? m : mn;
+        mx = m > mx ? m : mx;
+    }
+    long long n_lo = 0, n_hi = -1;
+    if (any) {
+        if (mn < 0) n_lo = (-mn + step - 1) / step;
+        const long long last = N - L - mx;  // last valid window start of the slowest channel
+        if (last >= 0) {
+            n_hi = last / step;
+            if (n_hi > n_corr - 1) n_hi = n_corr - 1;
+        }
+    }
+    lo[t] = (int)n_lo;
+    hi[t] = (int)n_hi;
+}
+
+// ---------------------------------------------------------------- sliding window energy
+constexpr int EN_THREADS = 256;
+constexpr int EN_BJ = 4096;  // window starts per block
+
+__device__ __forceinline__ double block_exclusive_scan(double v, double *warp_tot, double *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    double base = 0.0, tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < EN_THREADS / 32; w++) {
+        const double x = warp_tot[w];
+        if (w < wid) base += x;
+        tot += x;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(EN_THREADS)
+    mf_energy_kernel(const float *__restrict__ data, size_t N, size_t L, size_t n_win,
+                     float *__restrict__ energy, float *__restrict__ mean) {
+    extern __shared__ double sm[];
+    __shared__ double warp_tot[EN_THREADS / 32];
+    const size_t ch = blockIdx.y;
+    const size_t j0 = (size_t)blockIdx.x * EN_BJ;
+    if (j0 >= n_win) return;
+    const size_t nj = (n_win - j0 < (size_t)EN_BJ) ? (n_win - j0) : (size_t)EN_BJ;
+    const size_t span = nj + L - 1;  // data samples [j0, j0 + span)
+    const float *d = data + ch * N + j0;
+    double *P2 = sm;                                // span + 1 exclusive prefix of d^2
+    double *P1 = sm + (FULL ? span + 1 : 0);        // span + 1 exclusive prefix of d
+
+    const size_t run = (span + EN_THREADS - 1) / EN_THREADS;
+    const size_t a = (size_t)threadIdx.x * run;
+    const size_t b = (a + run < span) ? a + run : span;
+    double s2 = 0.0, s1 = 0.0;
+    for (size_t i = a; i < b; i++) {
+        const double v = (double)d[i];
+        s2 += v * v;
+        if (FULL) s1 += v;
+    }
+    double tot2, tot1 = 0.0;
+    double r2 = block_exclusive_scan(s2, warp_tot, &tot2);
+    double r1 = 0.0;
+    if (FULL) r1 = block_exclusive_scan(s1, warp_tot, &tot1);
+    for (size_t i = a; i < b; i++) {
+        const double v = (double)d[i];
+        P2[i] = r2;
+        r2 += v * v;
+        if (FULL) { P1[i] = r1; r1 += v; }
+    }
+    if (threadIdx.x == 0) {
+        P2[span] = tot2;
+        if (FULL) P1[span] = tot1;
+    }
+    __syncthreads();
+    float *e = energy + ch * n_win + j0;
+    float *m = FULL ? mean + ch * n_win + j0 : nullptr;
+    for (size_t j = threadIdx.x; j < nj; j += EN_THREADS) {
+        double ss = P2[j + L] - P2[j];
+        if (FULL) {
+            const double mu = (P1[j + L] - P1[j]) / (double)L;
+            ss -= (double)L * mu * mu;
+            m[j] = (float)mu;
+        }
+        e[j] = (float)(ss > 0.0 ? ss : 0.0);
+    }
+}
+
+int mf_prepass(const MfShape &sh, const float *d_templates, const int *d_moveouts,
+               const float *d_weights, const float *d_data, MfMeta meta, float *d_energy,
+               float *d_mean, cudaStream_t st) {
+    const size_t rows = sh.T * sh.SC();
+    {
+        const int warps = 8;
+        mf_template_stats_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(
+            d_templates, rows, sh.L, meta.sst, meta.sumt);
+        BPMF_LAUNCH_CHECK();
+    }
+    {
+        mf_bounds_kernel<<<(unsigned)((sh.T + 127) / 128), 128, 0, st>>>(
+            d_moveouts, d_weights, sh.T, sh.SC(), (long long)sh.N, (long long)sh.L,
+            (long long)sh.step, (long long)sh.n_corr, meta.lo, meta.hi);
+        BPMF_LAUNCH_CHECK();
+    }
+    if (d_energy) {
+        const size_t n_win = sh.N - sh.L + 1;
+        const bool full = sh.normalize != 0;
+        const size_t span_max = (size_t)EN_BJ + sh.L;
+        const size_t smem = sizeof(double) * span_max * (full ? 2 : 1);
+        BPMF_REQUIRE(smem <= 200 * 1024, "template too long for the energy pre-pass (L=%zu)", sh.L);
+        dim3 grid((unsigned)((n_win + EN_BJ - 1) / EN_BJ), (unsigned)sh.SC());
+        if (full) {
+            BPMF_CUDA(cudaFuncSetAttribute(mf_energy_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mf_energy_kernel<true><<<grid, EN_THREADS, smem, st>>>(d_data, sh.N, sh.L, n_win,
+                                                                    d_energy, d_mean);
+        } else {
+            BPMF_CUDA(cudaFuncSetAttribute(mf_energy_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mf_energy_kernel<false><<<grid, EN_THREADS, smem, st>>>(d_data, sh.N, sh.L, n_win,
+                                                                     d_energy, d_mean);
+        }
+        BPMF_LAUNCH_CHECK();
+    }
+    return BPMF_OK;
+}
+
+}  // namespace bpmf

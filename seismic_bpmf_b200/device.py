@@ -1,0 +1,163 @@
+"""Device-resident entry points: inputs and outputs are torch CUDA tensors, work is enqueued on
+torch's current stream through the ``*_dev`` functions of the C-ABI (include/bpmf_b200.h), with no
+host synchronisation.  PyTorch is plumbing only here (device memory + streams).
+"""
+import torch
+
+from . import _lib
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s" % (name, dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def mf_n_corr(n_samples_data, n_samples_template, step):
+    return int(_lib.load().bpmf_mf_n_corr(n_samples_data, n_samples_template, step))
+
+
+def mf_cc_pitch(n_corr):
+    """Row pitch (elements) used for device CC slabs: rows start on 256-byte boundaries."""
+    return (n_corr + 63) // 64 * 64
+
+
+class MatchedFilterPlan:
+    """Pre-allocated workspace + output slab for repeated device-resident matched-filter calls."""
+
+    def __init__(self, n_templates, n_stations, n_components, n_samples_template, n_samples_data,
+                 step=1, normalize="short", network_sum=True, precision="auto", device=None):
+        self.lib = _lib.load()
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.T, self.S, self.C = int(n_templates), int(n_stations), int(n_components)
+        self.L, self.N, self.step = int(n_samples_template), int(n_samples_data), int(step)
+        self.normalize = 1 if normalize == "full" else 0
+        self.network_sum = 1 if network_sum else 0
+        self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        self.n_corr = mf_n_corr(self.N, self.L, self.step)
+        self.resolved_precision = int(self.lib.bpmf_mf_resolve_precision(
+            self.L, self.step, self.normalize, self.network_sum, self.precision))
+        if self.resolved_precision <= 0:
+            raise _lib.BpmfError("precision %r is not available for this shape" % (precision,))
+        ws = int(self.lib.bpmf_mf_workspace_bytes(self.L, self.N, self.T, self.S, self.C, self.step,
+                                                  self.normalize, self.network_sum, self.precision))
+        self.workspace = torch.empty(max(ws, 256), dtype=torch.uint8, device=self.device)
+        if self.network_sum:
+            self.pitch = mf_cc_pitch(self.n_corr)
+            self.cc = torch.empty((self.T, self.pitch), dtype=torch.float32, device=self.device)
+        else:
+            self.pitch = 0
+            self.cc = torch.empty((self.T, self.n_corr, self.S, self.C), dtype=torch.float32,
+                                  device=self.device)
+
+    def run(self, templates, moveouts, weights, data):
+        """Enqueue one matched-filter pass; returns the (T, n_corr[, S, C]) CC view on the device."""
+        _chk(templates, torch.float32, "templates")
+        _chk(moveouts, torch.int32, "moveouts")
+        _chk(weights, torch.float32, "weights")
+        _chk(data, torch.float32, "data")
+        assert tuple(templates.shape) == (self.T, self.S, self.C, self.L)
+        assert tuple(data.shape) == (self.S, self.C, self.N)
+        assert tuple(moveouts.shape) == (self.T, self.S, self.C) == tuple(weights.shape)
+        rc = self.lib.bpmf_matched_filter_dev(
+            templates.data_ptr(), moveouts.data_ptr(), weights.data_ptr(), data.data_ptr(), self.step,
+            self.L, self.N, self.T, self.S, self.C, self.normalize, self.network_sum, self.precision,
+            self.workspace.data_ptr(), self.workspace.numel(), self.cc.data_ptr(), self.pitch,
+            _stream_ptr())
+        _lib.check(rc, "matched_filter_dev")
+        return self.cc[:, : self.n_corr] if self.network_sum else self.cc
+
+
+def matched_filter_dev(templates, moveouts, weights, data, step=1, normalize="short", network_sum=True,
+                       precision="auto"):
+    T, S, C, L = templates.shape
+    plan = MatchedFilterPlan(T, S, C, L, data.shape[-1], step, normalize, network_sum, precision,
+                             device=templates.device)
+    return plan.run(templates, moveouts, weights, data)
+
+
+class BeamformPlan:
+    def __init__(self, n_sources, n_stations, n_components, n_phases, n_samples, device=None):
+        self.lib = _lib.load()
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.K, self.S, self.C, self.P, self.N = map(int, (n_sources, n_stations, n_components, n_phases, n_samples))
+        ws = int(self.lib.bpmf_beam_workspace_bytes(self.K, self.S, self.C, self.P, self.N))
+        self.workspace = torch.empty(max(ws, 256), dtype=torch.uint8, device=self.device)
+        self.maxbeam = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        self.sources = torch.empty(self.N, dtype=torch.int32, device=self.device)
+
+    def _check(self, features, moveouts, weights_phases, weights_sources):
+        _chk(features, torch.float32, "features")
+        _chk(moveouts, torch.int32, "moveouts")
+        _chk(weights_phases, torch.float32, "weights_phases")
+        _chk(weights_sources, torch.float32, "weights_sources")
+        assert tuple(features.shape) == (self.S, self.C, self.N)
+        assert tuple(moveouts.shape) == (self.K, self.S, self.P)
+        assert tuple(weights_phases.shape) == (self.S, self.C, self.P)
+        assert tuple(weights_sources.shape) == (self.K, self.S)
+
+    def run_max(self, features, moveouts, weights_phases, weights_sources, out_of_bounds="strict",
+                source_offset=0):
+        self._check(features, moveouts, weights_phases, weights_sources)
+        rc = self.lib.bpmf_beamform_max_dev(
+            features.data_ptr(), moveouts.data_ptr(), weights_phases.data_ptr(),
+            weights_sources.data_ptr(), self.K, self.S, self.C, self.P, self.N,
+            1 if out_of_bounds == "flexible" else 0, int(source_offset), self.workspace.data_ptr(),
+            self.workspace.numel(), self.maxbeam.data_ptr(), self.sources.data_ptr(), _stream_ptr())
+        _lib.check(rc, "beamform_max_dev")
+        return self.maxbeam, self.sources
+
+    def run_full(self, features, moveouts, weights_phases, weights_sources, out_of_bounds="strict"):
+        self._check(features, moveouts, weights_phases, weights_sources)
+        beam = torch.empty((self.K, self.N), dtype=torch.float32, device=self.device)
+        rc = self.lib.bpmf_beamform_full_dev(
+            features.data_ptr(), moveouts.data_ptr(), weights_phases.data_ptr(),
+            weights_sources.data_ptr(), self.K, self.S, self.C, self.P, self.N,
+            1 if out_of_bounds == "flexible" else 0, self.workspace.data_ptr(), self.workspace.numel(),
+            beam.data_ptr(), _stream_ptr())
+        _lib.check(rc, "beamform_full_dev")
+        return beam
+
+
+def beam_merge_(max_a, arg_a, max_b, arg_b):
+    """In place a = better(a, b) with ties to the lower source index."""
+    rc = _lib.load().bpmf_beam_merge_dev(max_a.data_ptr(), arg_a.data_ptr(), max_b.data_ptr(),
+                                         arg_b.data_ptr(), max_a.numel(), _stream_ptr())
+    _lib.check(rc, "beam_merge_dev")
+    return max_a, arg_a
+
+
+def time_dependent_threshold_dev(series, gaussian_sample, num_dev, half_window_samp, shift_samp,
+                                 n_valid=None):
+    """Batched rms threshold on a (B, pitch) device slab (e.g. the CC slab of MatchedFilterPlan).
+
+    ``series`` is modified in place (zeros are replaced, as libc.c:606-612 does).  Returns the
+    (B, n) threshold tensor.
+    """
+    lib = _lib.load()
+    assert series.is_cuda and series.dtype == torch.float32 and series.dim() == 2
+    B = series.shape[0]
+    n = int(series.shape[1] if n_valid is None else n_valid)
+    pitch = series.stride(0)
+    assert series.stride(1) == 1
+    g = _chk(gaussian_sample, torch.float32, "gaussian_sample")
+    assert g.numel() == 500
+    ws = int(lib.bpmf_threshold_workspace_bytes(B, n, half_window_samp, shift_samp))
+    workspace = torch.empty(max(ws, 256), dtype=torch.uint8, device=series.device)
+    thr = torch.empty((B, n), dtype=torch.float32, device=series.device)
+    rc = lib.bpmf_time_dependent_threshold_dev(series.data_ptr(), pitch, B, g.data_ptr(), float(num_dev),
+                                               n, int(half_window_samp), int(shift_samp),
+                                               workspace.data_ptr(), workspace.numel(), thr.data_ptr(),
+                                               n, _stream_ptr())
+    _lib.check(rc, "time_dependent_threshold_dev")
+    return thr

@@ -1,0 +1,116 @@
+"""Multi-GPU sharding of the two hot paths (one process per GPU, torch.distributed plumbing).
+
+* matched filter: templates are independent -> block-partition T over the ranks, replicate the
+  traces, one ``all_gather`` of the per-shard (T/G, n_corr) CC slabs at the end (SURVEY.md 8e;
+  station chunks are additive, BPMF/similarity_search.py:517-538, but summing them would need an
+  all-reduce of the whole slab, 8x the traffic).
+* beamforming, reduce="max": sources are independent up to the final max -> block-partition K,
+  every rank reports global source ids, one ``all_gather`` of (max, argmax) pairs followed by a
+  local G-way select with ties to the lowest source index.
+
+The compute step is injectable (``compute=``) so the partition/gather/merge logic is exercised on
+CPU with the ``gloo`` backend in tests; the default compute is the CUDA path (no CPU fallback).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous block partition of range(n): first (n % world) ranks get one extra item."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _mf_compute_cuda(templates, moveouts, weights, data, step, normalize, precision):
+    from . import device as dev
+
+    return dev.matched_filter_dev(templates, moveouts, weights, data, step=step, normalize=normalize,
+                                  network_sum=True, precision=precision)
+
+
+def matched_filter_sharded(templates, moveouts, weights, data, step=1, normalize="short",
+                           precision="auto", group=None, gather=True, compute=None):
+    """Template-sharded matched filter.
+
+    Every rank passes the FULL (T,S,C,L) templates / (T,S,C) moveouts, weights and the (S,C,N)
+    traces (torch tensors on its own device).  Returns the (T, n_corr) CC sums on every rank when
+    ``gather`` is true, else ``(local_cc, (t_lo, t_hi))``.
+    """
+    rank, world = _world(group)
+    T = templates.shape[0]
+    lo, hi = shard_bounds(T, rank, world)
+    compute = compute or _mf_compute_cuda
+    n_corr = (data.shape[-1] - templates.shape[-1]) // step + 1
+    if hi > lo:
+        local = compute(templates[lo:hi].contiguous(), moveouts[lo:hi].contiguous(),
+                        weights[lo:hi].contiguous(), data, step, normalize, precision)
+    else:
+        local = torch.zeros((0, n_corr), dtype=torch.float32, device=data.device)
+    if not gather:
+        return local, (lo, hi)
+    if world == 1:
+        return local
+    # equal-sized slabs for the collective: pad the short shards with one zero row
+    rows = (T + world - 1) // world
+    slab = torch.zeros((rows, n_corr), dtype=torch.float32, device=data.device)
+    slab[: hi - lo] = local
+    full = torch.empty((world * rows, n_corr), dtype=torch.float32, device=data.device)
+    dist.all_gather_into_tensor(full, slab, group=group)
+    out = torch.empty((T, n_corr), dtype=torch.float32, device=data.device)
+    for r in range(world):
+        a, b = shard_bounds(T, r, world)
+        out[a:b] = full[r * rows: r * rows + (b - a)]
+    return out
+
+
+def merge_max_argmax(maxes, args):
+    """(G,N) per-shard maxima and GLOBAL source ids -> (N,), (N,) with ties to the lowest id."""
+    best = maxes.max(dim=0).values
+    big = torch.iinfo(args.dtype).max
+    cand = torch.where(maxes == best.unsqueeze(0), args, torch.full_like(args, big))
+    return best, cand.min(dim=0).values
+
+
+def _beam_compute_cuda(features, moveouts, weights_phases, weights_sources, out_of_bounds, source_offset):
+    from . import device as dev
+
+    K, S, P = moveouts.shape
+    plan = dev.BeamformPlan(K, S, features.shape[1], P, features.shape[-1], device=features.device)
+    return plan.run_max(features, moveouts, weights_phases, weights_sources, out_of_bounds, source_offset)
+
+
+def beamform_max_sharded(features, moveouts, weights_phases, weights_sources, out_of_bounds="strict",
+                         group=None, compute=None):
+    """Source-sharded beamforming with reduce="max"; returns (maxbeam, maxbeam_sources) on every rank."""
+    rank, world = _world(group)
+    K = moveouts.shape[0]
+    N = features.shape[-1]
+    lo, hi = shard_bounds(K, rank, world)
+    compute = compute or _beam_compute_cuda
+    if hi > lo:
+        mb, arg = compute(features, moveouts[lo:hi].contiguous(), weights_phases,
+                          weights_sources[lo:hi].contiguous(), out_of_bounds, lo)
+    else:  # an empty shard must never win: -inf, id = int32 max
+        mb = torch.full((N,), float("-inf"), dtype=torch.float32, device=features.device)
+        arg = torch.full((N,), torch.iinfo(torch.int32).max, dtype=torch.int32, device=features.device)
+    if world == 1:
+        return mb, arg
+    packed_m = torch.empty((world, N), dtype=torch.float32, device=features.device)
+    packed_a = torch.empty((world, N), dtype=torch.int32, device=features.device)
+    dist.all_gather_into_tensor(packed_m, mb.contiguous(), group=group)
+    dist.all_gather_into_tensor(packed_a, arg.contiguous(), group=group)
+    if features.is_cuda:
+        from . import device as dev
+
+        best, barg = packed_m[0].clone(), packed_a[0].clone()
+        for r in range(1, world):
+            dev.beam_merge_(best, barg, packed_m[r], packed_a[r])
+        return best, barg
+    return merge_max_argmax(packed_m, packed_a)
