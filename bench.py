@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- CC-sum throughput of the matched-filter hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N ...            # CPU oracle on the host cores
+    torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU
+
+A "step" is one pass of the matched filter over one batch of synthetic input.  At N = 1 the
+workload is BASELINE.json configs[1] (500 templates x 16 stations x 3 channels, 8 s templates, one
+day @ 100 Hz, float32).  At N > 1 every rank processes that same per-GPU workload on its own shard
+of templates (weak scaling: 500*N templates, traces replicated) and the per-shard CC slabs are
+exchanged with NCCL all-gathers (chunked, because the gathered CC of configs[3] does not fit one
+GPU -- SURVEY.md 8e).
+
+metric = CC-sum GSamples/s = templates x channels x n_corr / seconds / 1e9.
+  value : inputs resident in HBM when the timed region starts (device entry point, CUDA events).
+  e2e   : same metric through the reference-facing call fast_matched_filter.matched_filter(...) with
+          pinned HOST buffers, host<->device copies inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20240726
+CFG2 = dict(T=500, S=16, C=3, L=800, N=8640000, step=1)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "fp16x3"])
+    ap.add_argument("--templates", type=int, default=CFG2["T"], help="templates per GPU")
+    ap.add_argument("--samples", type=int, default=CFG2["N"], help="trace length in samples")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tensor_tflops=p["bf16_tflops"],
+                    tensor_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    sm_max_mhz=p.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(hbm_gbs=6650.0, tensor_tflops=1590.0, tensor_tflops_sustained=1400.0, sm_max_mhz=1965.0,
+                source="fallback")
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ synthetic workload
+def make_inputs_device(torch, T, S, Cc, L, N, seed, device):
+    """Traces ~N(0,1) per-channel RMS-normalised (BPMF/similarity_search.py:181-185) with a 10 000
+    sample zero gap on one station; templates ~N(0,1) demeaned + normalised (BPMF/dataset.py:4160-4165),
+    1 % cut from the data (planted detections); int32 moveouts U{-100..3000}; weights all-ones
+    row-normalised (BPMF/similarity_search.py:469-472).  SURVEY.md 8(d)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    data = torch.randn((S, Cc, N), generator=g, device=device, dtype=torch.float32)
+    data[S // 2, :, N // 3: N // 3 + 10000] = 0.0
+    std = data.std(dim=-1, keepdim=True)
+    std[std == 0] = 1.0
+    data /= std
+    templates = torch.randn((T, S, Cc, L), generator=g, device=device, dtype=torch.float32)
+    templates -= templates.mean(dim=-1, keepdim=True)
+    templates /= templates.std(dim=-1, keepdim=True)
+    mv_hi = int(min(3000, max(0, (N - L) // 4)))
+    moveouts = torch.randint(-100, mv_hi + 1, (T, S, Cc), generator=g, device=device, dtype=torch.int32)
+    planted = {}
+    for t in range(0, T, 100):
+        i0 = 5000 + 37 * t
+        if i0 + mv_hi + L >= N // 3:
+            break
+        idx = (i0 + moveouts[t].long()).reshape(S, Cc, 1) + torch.arange(L, device=device).reshape(1, 1, L)
+        templates[t] = torch.gather(data, 2, idx)
+        planted[t] = i0
+    weights = torch.full((T, S, Cc), 1.0 / (S * Cc), device=device, dtype=torch.float32)
+    return templates.contiguous(), moveouts.contiguous(), weights, data.contiguous(), planted
+
+
+def algorithmic_bytes(T, S, Cc, L, N, n_corr):
+    """compulsory traffic of one matched-filter pass."""
+    return 4 * S * Cc * N + 4 * T * S * Cc * L + 8 * T * S * Cc + 4 * T * n_corr
+
+
+# ------------------------------------------------------------------ CPU oracle arm
+def cpu_sample_throughput(seconds, S, Cc, L, seed=SEED):
+    """Time oracle/mf_oracle.c (C99 + OpenMP, all host threads) on a bounded sample of the same
+    workload: S x C channels, L-sample templates, step 1; the number of templates and the trace
+    length are scaled from a calibration run so the sample takes about `seconds`."""
+    from oracle import cpu
+
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+
+    def run(T, N):
+        data = rng.standard_normal((S, Cc, N)).astype(np.float32)
+        tp = rng.standard_normal((T, S, Cc, L)).astype(np.float32)
+        mv = rng.integers(0, min(3000, N // 8) + 1, (T, S, Cc)).astype(np.int32)
+        w = np.full((T, S, Cc), 1.0 / (S * Cc), np.float32)
+        t0 = time.perf_counter()
+        cc = cpu.matched_filter(tp, mv, w, data, 1)
+        dt = time.perf_counter() - t0
+        return T * S * Cc * cc.shape[1] / dt / 1e9, dt
+
+    rate, dt = run(1, 60000)
+    units = rate * 1e9 * seconds
+    N = 400000
+    T = int(max(1, min(64, units / (S * Cc * (N - L + 1)))))
+    rate, dt = run(T, N)
+    return rate, cores, "%d templates x %d stations x %d channels x %d samples (L=%d, step 1), %.1f s" % (
+        T, S, Cc, N, L, dt)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    T, S, Cc, L, N = args.templates, CFG2["S"], CFG2["C"], CFG2["L"], args.samples
+    rates, sample = [], ""
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        rate, cores, sample = cpu_sample_throughput(per_step, S, Cc, L, seed=SEED + i)
+        if i >= args.warmup:
+            rates.append(rate)
+    value = float(np.mean(rates))
+    n_corr = N - L + 1
+    line = {
+        "impl": "reference", "metric": "CC-sum GSamples/s (templates x traces x steps)", "value": value,
+        "unit": "GSamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (T * S * Cc * n_corr / 1e9) / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "matched_filter cfg2: %d templates x %d stations x %d ch, L=%d, N=%d, step 1"
+                   % (T, S, Cc, L, N), "note": "ms_per_step extrapolated from the bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "GSamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from seismic_bpmf_b200 import _lib, device as dev, fast_matched_filter as fmf
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    pk = peaks()
+    T, S, Cc, L, N, step = args.templates, CFG2["S"], CFG2["C"], CFG2["L"], args.samples, 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # rank r owns templates [r*T, (r+1)*T) of the global 500*N set: different seeds per rank
+    tp, mv, w, data, planted = make_inputs_device(torch, T, S, Cc, L, N, SEED + rank, device)
+    if world > 1:  # traces are replicated: take rank 0's
+        dist.broadcast(data, src=0)
+        planted = {}
+    plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, precision=args.precision, device=device)
+    n_corr = plan.n_corr
+    prec_name = {1: "fp32", 2: "fp16", 3: "fp16x3"}[plan.resolved_precision]
+    units = T * S * Cc * n_corr  # per rank, per step
+
+    gather_rows = 25
+    gbuf = None
+    if world > 1:
+        gbuf = torch.empty(world * gather_rows * plan.pitch, dtype=torch.float32, device=device)
+
+    def step_fn():
+        cc = plan.run(tp, mv, w, data)
+        if world > 1:  # the exchange step: chunked all-gather of the per-shard CC slab
+            for t0 in range(0, T, gather_rows):
+                rows = min(gather_rows, T - t0)
+                src = plan.cc[t0: t0 + rows].reshape(-1)
+                dist.all_gather_into_tensor(gbuf[: world * rows * plan.pitch], src)
+        return cc
+
+    for _ in range(args.warmup):
+        step_fn()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.bpmf_set_kernel_timing(1)
+    launches0 = lib.bpmf_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_fn()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = int(lib.bpmf_launch_count() - launches0)
+    buf = (C.c_float * 256)()
+    nk = lib.bpmf_main_kernel_times(buf, 256)
+    lib.bpmf_set_kernel_timing(0)
+    kernel_ms = float(np.mean([buf[i] for i in range(nk)])) if nk else None
+    clocks = sampler.stop() if rank == 0 else None
+
+    t_ms = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = world * units / (ms_per_step * 1e-3) / 1e9
+
+    # ---- parity spot check (untimed): first template against the oracle on a trace slice
+    parity = None
+    if rank == 0:
+        from oracle import cpu
+
+        n_slice = min(N, 200000)
+        cc_dev = plan.cc[:2, :n_corr].cpu().numpy()
+        want = cpu.matched_filter(tp[:2].cpu().numpy(), mv[:2].cpu().numpy(), w[:2].cpu().numpy(),
+                                  data[:, :, :n_slice].cpu().numpy(), 1)
+        hi = n_slice - L - int(mv[:2].max().item()) - 1
+        lo = max(0, -int(mv[:2].min().item()))
+        err = float(np.abs(cc_dev[:, lo:hi] - want[:, lo:hi]).max())
+        ok_plant = all(int(torch.argmax(plan.cc[t, :n_corr]).item()) == i0 for t, i0 in planted.items())
+        parity = {"max_abs_err_vs_oracle": err, "tolerance": 1e-4, "planted_detections_recovered": bool(ok_plant),
+                  "sample": "templates 0-1 x first %d samples" % n_slice}
+
+    # ---- end-to-end arm: the reference-facing call with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        h = {}
+        for name, ten in (("tp", tp), ("mv", mv), ("w", w), ("data", data)):
+            pinned = torch.empty(ten.shape, dtype=ten.dtype, pin_memory=True)
+            pinned.copy_(ten)
+            h[name] = pinned.numpy()
+        out_pinned = torch.empty((T, n_corr), dtype=torch.float32, pin_memory=True)
+        out_np = out_pinned.numpy()
+        h2d = sum(h[k].nbytes for k in h)
+        d2h = out_np.nbytes
+        del plan  # the host entry point allocates its own device buffers
+        if gbuf is not None:
+            del gbuf
+        torch.cuda.empty_cache()
+        fmf.matched_filter(h["tp"], h["mv"], h["w"], h["data"], step, arch="gpu", precision=args.precision,
+                           check_zeros=False, out=out_np)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            fmf.matched_filter(h["tp"], h["mv"], h["w"], h["data"], step, arch="gpu", precision=args.precision,
+                               check_zeros=False, out=out_np)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        t_e = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * units / float(t_e.item()) / 1e9, "unit": "GSamples/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "ms_per_step": 1e3 * float(t_e.item()), "host_buffers": "pinned"}
+
+    if rank != 0:
+        return
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, sample = cpu_sample_throughput(args.cpu_seconds, S, Cc, L)
+        cpu_base = {"value": rate, "unit": "GSamples/s", "cores": cores, "kind": "port", "sample": sample}
+
+    flops = 2.0 * L * units
+    roof = None
+    if kernel_ms:
+        sec = kernel_ms * 1e-3
+        tflops = flops / sec / 1e12
+        if plan_is_tensor(prec_name):
+            mult = 3.0 if prec_name == "fp16x3" else 1.0
+            roof = {"bound": "tensor", "achieved": tflops * mult, "peak": pk["tensor_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": tflops * mult / pk["tensor_tflops_sustained"], "traffic": None,
+                    "peak_source": pk["source"] + " (sustained bf16 cuBLAS; fp16 runs at the same tensor rate)",
+                    "algorithmic_tflops": tflops, "kernel_ms": kernel_ms, "kernel": "mf_tc_kernel"}
+        else:
+            sm_mhz = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
+            peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            roof = {"bound": "fp32-fma", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
+                    "traffic": None, "peak_source": "148 SM x 128 lanes x 2 x measured SM clock (no tensor cores on this path)",
+                    "kernel_ms": kernel_ms, "kernel": "mf_fp32_step1_kernel"}
+        ab = algorithmic_bytes(T, S, Cc, L, N, n_corr)
+        roof["hbm"] = {"algorithmic_bytes": ab, "achieved_gbs": ab / sec / 1e9, "peak_gbs": pk["hbm_gbs"],
+                       "frac": ab / sec / 1e9 / pk["hbm_gbs"]}
+
+    line = {
+        "metric": "CC-sum GSamples/s (templates x traces x steps)", "value": value, "unit": "GSamples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if prec_name == "fp32" else "f16",
+        "data": "synthetic",
+        "config": {"workload": "matched_filter cfg2 per GPU: %d templates x %d stations x %d ch, L=%d, N=%d, step 1"
+                   % (T, S, Cc, L, N), "precision": prec_name, "templates_total": T * world,
+                   "l2": "inputs (%.2f GB) and output (%.2f GB) exceed the 126 MB L2" % (
+                       (data.numel() * 4 + tp.numel() * 4) / 1e9, T * n_corr * 4 / 1e9),
+                   "collective": "chunked NCCL all-gather of per-shard CC slabs" if world > 1 else "none"},
+        "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "parity": parity,
+    }
+    print(json.dumps(line))
+
+
+def plan_is_tensor(prec_name):
+    return prec_name in ("fp16", "fp16x3")
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        try:
+            run_ours(args, rank, world, local_rank)
+        finally:
+            dist.destroy_process_group()
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,13 @@ const char *bpmf_version(void);
 /* number of kernel launches issued by this library since process start (all threads) */
 unsigned long long bpmf_launch_count(void);
 
+/* Optional instrumentation for bench.py: while enabled, the dominant kernel of every
+ * bpmf_matched_filter_dev / bpmf_beamform_*_dev call made by the calling thread is bracketed by
+ * CUDA events on the launching stream (up to 256 launches).  bpmf_main_kernel_times() waits for
+ * them, writes their durations in milliseconds and returns how many; it also clears the list. */
+void bpmf_set_kernel_timing(int enable);
+int bpmf_main_kernel_times(float *ms, int capacity);
+
 /* ---------------------------------------------------------------- (3) BPMF/GPU.cu:7-24 */
 void caract_GPU(void);
 

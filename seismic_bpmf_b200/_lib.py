@@ -31,6 +31,8 @@ _SIGNATURES = {
     "bpmf_version": (C.c_char_p, []),
     "bpmf_device_count": (C.c_int, []),
     "bpmf_launch_count": (C.c_ulonglong, []),
+    "bpmf_set_kernel_timing": (None, [C.c_int]),
+    "bpmf_main_kernel_times": (C.c_int, [fp, C.c_int]),
     "caract_GPU": (None, []),
     "bpmf_mf_n_corr": (z, [z, z, z]),
     "bpmf_matched_filter": (C.c_int, [fp, ip, fp, fp, z, z, z, z, z, z, C.c_int, C.c_int, C.c_int, fp]),

@@ -20,6 +20,27 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static std::atomic<int> g_timing{0};
+constexpr int TIMER_RING = 256;
+static thread_local cudaEvent_t g_ev[TIMER_RING][2];
+static thread_local int g_ev_created = 0, g_ev_count = 0;
+
+MainKernelTimer::MainKernelTimer(cudaStream_t s) : st(s), on(g_timing.load() != 0) {
+    if (!on) return;
+    if (g_ev_count >= TIMER_RING) { on = false; return; }
+    if (g_ev_count >= g_ev_created) {
+        cudaEventCreate(&g_ev[g_ev_created][0]);
+        cudaEventCreate(&g_ev[g_ev_created][1]);
+        g_ev_created++;
+    }
+    cudaEventRecord(g_ev[g_ev_count][0], st);
+}
+MainKernelTimer::~MainKernelTimer() {
+    if (!on) return;
+    cudaEventRecord(g_ev[g_ev_count][1], st);
+    g_ev_count++;
+}
+
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;
@@ -73,6 +94,25 @@ using namespace bpmf;
 extern "C" const char *bpmf_last_error(void) { return g_err; }
 extern "C" const char *bpmf_version(void) { return "bpmf_b200 r1 sm_100a"; }
 extern "C" unsigned long long bpmf_launch_count(void) { return g_launches.load(); }
+
+extern "C" void bpmf_set_kernel_timing(int enable) {
+    g_timing.store(enable ? 1 : 0);
+    g_ev_count = 0;
+}
+extern "C" int bpmf_main_kernel_times(float *ms, int capacity) {
+    int n = 0;
+    for (int i = 0; i < g_ev_count && n < capacity; i++) {
+        float t = -1.f;
+        if (cudaEventSynchronize(g_ev[i][1]) != cudaSuccess ||
+            cudaEventElapsedTime(&t, g_ev[i][0], g_ev[i][1]) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        ms[n++] = t;
+    }
+    g_ev_count = 0;
+    return n;
+}
 
 extern "C" int bpmf_device_count(void) {
     int n = 0;

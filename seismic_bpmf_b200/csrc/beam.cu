@@ -246,6 +246,7 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
     if (reduce_max) {
         BPMF_CUDA(cudaMemsetAsync(b.keys, 0, sizeof(unsigned long long) * N, st));
         if (K > 0) {
+            MainKernelTimer timer(st);
             // enough source chunks to fill the machine when the time axis is short
             const size_t want = (size_t)num_sms() * 4;
             size_t n_chunks = (n_tiles >= want) ? 1 : (want + n_tiles - 1) / n_tiles;
@@ -272,6 +273,7 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
         }
         BPMF_CUDA(cudaFuncSetAttribute(beam_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MainKernelTimer timer(st);
         dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
         beam_kernel<false><<<grid, B_THREADS, smem, st>>>(b.U, d_tau, d_beta, b.tlo, b.thi, K, (int)S,
                                                           (int)P, (long long)N, flexible ? 0 : 1,

@@ -43,6 +43,14 @@ inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_o
         }                                                                                 \
     } while (0)
 
+// brackets the dominant kernel with events when bpmf_set_kernel_timing(1) is active
+struct MainKernelTimer {
+    cudaStream_t st;
+    bool on;
+    explicit MainKernelTimer(cudaStream_t s);
+    ~MainKernelTimer();
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // bump allocator over the caller-provided device workspace (256-byte granules)

@@ -243,6 +243,7 @@ int mf_fp32_run(const MfShape &sh, const float *d_templates, const int *d_moveou
     const bool full = sh.normalize != 0, netsum = sh.network_sum != 0;
     const size_t SMEM_MAX = 220 * 1024;
     int rc;
+    MainKernelTimer timer(st);
     if (sh.step == 1) {
         const int nkb = (int)((sh.L + 3) / 4);
         const size_t smem = sizeof(float) * ((size_t)pad_idx(F_TI + 4 * nkb + 16) + 4 * (size_t)nkb);

@@ -61,8 +61,9 @@ def matched_filter_sharded(templates, moveouts, weights, data, step=1, normalize
     rows = (T + world - 1) // world
     slab = torch.zeros((rows, n_corr), dtype=torch.float32, device=data.device)
     slab[: hi - lo] = local
-    full = torch.empty((world * rows, n_corr), dtype=torch.float32, device=data.device)
-    dist.all_gather_into_tensor(full, slab, group=group)
+    full = torch.empty(world * rows * n_corr, dtype=torch.float32, device=data.device)
+    dist.all_gather_into_tensor(full, slab.view(-1), group=group)
+    full = full.view(world * rows, n_corr)
     out = torch.empty((T, n_corr), dtype=torch.float32, device=data.device)
     for r in range(world):
         a, b = shard_bounds(T, r, world)
@@ -102,10 +103,11 @@ def beamform_max_sharded(features, moveouts, weights_phases, weights_sources, ou
         arg = torch.full((N,), torch.iinfo(torch.int32).max, dtype=torch.int32, device=features.device)
     if world == 1:
         return mb, arg
-    packed_m = torch.empty((world, N), dtype=torch.float32, device=features.device)
-    packed_a = torch.empty((world, N), dtype=torch.int32, device=features.device)
-    dist.all_gather_into_tensor(packed_m, mb.contiguous(), group=group)
-    dist.all_gather_into_tensor(packed_a, arg.contiguous(), group=group)
+    packed_m = torch.empty(world * N, dtype=torch.float32, device=features.device)
+    packed_a = torch.empty(world * N, dtype=torch.int32, device=features.device)
+    dist.all_gather_into_tensor(packed_m, mb.contiguous().view(-1), group=group)
+    dist.all_gather_into_tensor(packed_a, arg.contiguous().view(-1), group=group)
+    packed_m, packed_a = packed_m.view(world, N), packed_a.view(world, N)
     if features.is_cuda:
         from . import device as dev
 

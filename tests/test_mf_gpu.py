@@ -1,0 +1,196 @@
+"""GPU parity tests of the matched filter, through the C-ABI (host-pointer entry point) and the
+device-resident entry point, against the CPU oracle on the same seeded inputs.  Tolerance: the
+|dCC| < 1e-4 float32 bound of BASELINE.json's north_star, written once as TOL."""
+import numpy as np
+import pytest
+
+from oracle import cpu, numpy_ref
+from seismic_bpmf_b200 import _lib, fast_matched_filter as fmf
+from tests import _synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _precisions(L, step=1, normalize="short", network_sum=True):
+    lib = _lib.load()
+    out = ["fp32"]
+    for name in ("fp16", "fp16x3"):
+        if lib.bpmf_mf_resolve_precision(L, step, 1 if normalize == "full" else 0, 1 if network_sum else 0,
+                                         _lib.PRECISIONS[name]) > 0:
+            out.append(name)
+    return out
+
+
+def _tol(prec):
+    return 2e-6 if prec in ("fp32", "fp16x3") else TOL
+
+
+def test_cfg1_shape_vs_oracle():
+    """BASELINE.json configs[0]: 1 template x 4 stations x 3 channels, 1 h @ 50 Hz, L = 400."""
+    tp, mv, w, d, planted = _synth.mf_case(1, 4, 3, 400, 180000)
+    want = cpu.matched_filter(tp, mv, w, d, 1)
+    for prec in _precisions(400):
+        got = fmf.matched_filter(tp, mv, w, d, 1, arch="gpu", precision=prec, check_zeros=False)
+        assert got.shape == want.shape == (1, 180000 - 400 + 1)
+        assert got.dtype == np.float32 and got.flags.writeable
+        err = np.abs(got - want).max()
+        assert err < _tol(prec), (prec, err)
+        assert np.array_equal(got == 0, want == 0), prec
+        for t, i0 in planted.items():
+            assert got[t].argmax() == i0 and abs(got[t, i0] - w[t].sum()) < _tol(prec) + 1e-6
+
+
+@pytest.mark.parametrize("T,S,C,L,N", [(7, 5, 3, 200, 30011), (33, 3, 2, 800, 20000), (2, 2, 1, 37, 4133),
+                                       (17, 6, 3, 800, 9000)])
+def test_vs_oracle_shapes(T, S, C, L, N):
+    tp, mv, w, d, _ = _synth.mf_case(T, S, C, L, N, seed=T * 131 + L, sparse_weights=(T % 2 == 1))
+    want = cpu.matched_filter(tp, mv, w, d, 1)
+    for prec in _precisions(L):
+        got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
+        err = np.abs(got - want).max()
+        assert err < _tol(prec), (prec, err)
+        assert np.array_equal(got == 0, want == 0), prec
+
+
+def test_float64_brute_force_agreement():
+    tp, mv, w, d, _ = _synth.mf_case(3, 4, 3, 128, 12000, seed=99)
+    want = numpy_ref.matched_filter(tp, mv, w, d, 1)
+    for prec in _precisions(128):
+        got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
+        assert np.abs(got - want).max() < _tol(prec), prec
+
+
+@pytest.mark.parametrize("step", [2, 3, 8, 25])
+def test_step_is_a_subsampling(step):
+    tp, mv, w, d, _ = _synth.mf_case(4, 3, 3, 100, 15000, seed=5)
+    base = fmf.matched_filter(tp, mv, w, d, 1, precision="fp32", check_zeros=False)
+    for prec in _precisions(100, step=step):
+        got = fmf.matched_filter(tp, mv, w, d, step, precision=prec, check_zeros=False)
+        assert got.shape == (4, (15000 - 100) // step + 1)
+        assert np.abs(got - base[:, ::step]).max() < _tol(prec), prec
+    assert np.abs(fmf.matched_filter(tp, mv, w, d, step, precision="fp32", check_zeros=False) -
+                  cpu.matched_filter(tp, mv, w, d, step)).max() < 2e-6
+
+
+@pytest.mark.parametrize("step", [1, 4])
+def test_normalize_full(step):
+    tp, mv, w, d, _ = _synth.mf_case(3, 3, 2, 150, 9000, seed=6)
+    d = d + 0.7  # non-zero mean so that "full" differs from "short"
+    want = cpu.matched_filter(tp, mv, w, d, step, normalize="full")
+    got = fmf.matched_filter(tp, mv, w, d, step, normalize="full", check_zeros=False)
+    assert np.abs(got - want).max() < 1e-5
+    short = fmf.matched_filter(tp, mv, w, d, step, check_zeros=False)
+    assert np.abs(short - want).max() > 1e-3
+
+
+def test_network_sum_false_layout():
+    tp, mv, w, d, _ = _synth.mf_case(3, 4, 2, 64, 5000, seed=7)
+    mv[:] = 0  # as BPMF/dataset.py:4778 does
+    got = fmf.matched_filter(tp, mv, w, d, 1, network_sum=False, check_zeros=False)
+    want = cpu.matched_filter(tp, mv, w, d, 1, network_sum=False)
+    assert got.shape == (3, 5000 - 64 + 1, 4, 2)
+    assert np.abs(got - want).max() < 2e-6
+    summed = fmf.matched_filter(tp, mv, w, d, 1, precision="fp32", check_zeros=False)
+    assert np.abs((got * w[:, None]).sum(axis=(2, 3)) - summed).max() < 1e-5
+
+
+def test_known_answers_and_invariances():
+    tp, mv, w, d, planted = _synth.mf_case(6, 4, 3, 256, 40000, seed=8)
+    for prec in _precisions(256):
+        tol = _tol(prec)
+        cc = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
+        assert np.isfinite(cc).all()
+        for t, i0 in planted.items():
+            assert abs(cc[t, i0] - w[t].sum()) < tol + 1e-6 and cc[t].argmax() == i0
+        assert np.all(np.abs(cc) <= np.abs(w).sum(axis=(1, 2))[:, None] + tol)
+        assert np.abs(fmf.matched_filter(tp, mv, w, 1000.0 * d, 1, precision=prec, check_zeros=False) - cc).max() < 2 * tol
+        assert np.abs(fmf.matched_filter(0.01 * tp, mv, w, d, 1, precision=prec, check_zeros=False) - cc).max() < 2 * tol
+        chunks = fmf.matched_filter(tp[:, :2], mv[:, :2], w[:, :2], d[:2], 1, precision=prec, check_zeros=False) + \
+            fmf.matched_filter(tp[:, 2:], mv[:, 2:], w[:, 2:], d[2:], 1, precision=prec, check_zeros=False)
+        live = cc != 0
+        assert np.abs(chunks - cc)[live].max() < 2 * tol  # additivity (similarity_search.py:517-538)
+        zeros = fmf.matched_filter(tp, mv, w, np.zeros_like(d), 1, precision=prec, check_zeros=False)
+        assert np.all(zeros == 0.0)
+
+
+def test_bounds_negative_moveouts_and_zero_weight_channels():
+    tp, mv, w, d, _ = _synth.mf_case(3, 3, 2, 80, 6000, seed=9, plant=False)
+    mv[0, 0, 0], mv[0, 1, 1] = -53, 977
+    mv[2] = -5
+    w[1, 2, :] = 0
+    tp[1, 2, :] = np.nan  # must never be touched
+    mv[1, 2, :] = 10 ** 6  # nor constrain the bounds
+    want = cpu.matched_filter(tp, mv, w, d, 1)
+    for prec in _precisions(80):
+        got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
+        assert np.isfinite(got).all()
+        assert np.all(got[0, :53] == 0) and got[0, 53] != 0
+        last = 6000 - 80 - 977
+        assert got[0, last] != 0 and np.all(got[0, last + 1:] == 0)
+        assert np.abs(got - want).max() < _tol(prec)
+
+
+def test_edge_shapes():
+    rng = np.random.default_rng(0)
+    # N == L: a single correlation
+    tp = rng.standard_normal((2, 1, 1, 50)).astype(np.float32)
+    d = rng.standard_normal((1, 1, 50)).astype(np.float32)
+    mv = np.zeros((2, 1, 1), np.int32)
+    w = np.ones((2, 1, 1), np.float32)
+    got = fmf.matched_filter(tp, mv, w, d, 1, check_zeros=False)
+    assert got.shape == (2, 1)
+    assert np.abs(got - cpu.matched_filter(tp, mv, w, d, 1)).max() < 2e-6
+    # all-zero weights for one template -> a zero row (BPMF skips them, similarity_search.py:510-512)
+    w[1] = 0
+    got = fmf.matched_filter(tp, mv, w, d, 1, check_zeros=False)
+    assert np.all(got[1] == 0)
+    # empty template set
+    got = fmf.matched_filter(tp[:0], mv[:0], w[:0], d, 1, check_zeros=False)
+    assert got.shape == (0, 1)
+    # 2-D moveouts broadcast over components; non-contiguous / float64 inputs are canonicalised
+    tp3 = rng.standard_normal((2, 2, 3, 40))
+    d3 = rng.standard_normal((2, 3, 900))
+    mv2 = rng.integers(0, 50, (2, 2))
+    w3 = np.ones((2, 2, 3))
+    got = fmf.matched_filter(tp3, mv2, w3, d3[:, :, ::1], 1, check_zeros=False)
+    want = cpu.matched_filter(tp3, mv2, w3, d3, 1)
+    assert np.abs(got - want).max() < 2e-6
+    # tiny amplitudes collapse to exact zero through the stability guard
+    got = fmf.matched_filter(tp3 * 1e-6, mv2, w3, d3 * 1e-6, 1, check_zeros=False)
+    assert np.all(got == 0)
+
+
+def test_upstream_symbol_and_check_zeros_message(capsys):
+    import ctypes as C
+
+    tp, mv, w, d, _ = _synth.mf_case(2, 3, 2, 60, 5000, seed=10)
+    lib = _lib.load()
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    n_corr = 5000 - 60 + 1
+    out = np.zeros((2, n_corr), np.float32)
+    sst = np.sum(tp ** 2, axis=-1).astype(np.float32)
+    lib.matched_filter(tp.ctypes.data_as(fp), sst.ctypes.data_as(fp), mv.ctypes.data_as(ip), d.ctypes.data_as(fp),
+                       w.ctypes.data_as(fp), 1, 60, 5000, 2, 3, 2, n_corr, 0, out.ctypes.data_as(fp))
+    assert np.abs(out - cpu.matched_filter(tp, mv, w, d, 1)).max() < TOL
+    d[:, :, 1000:2000] = 0
+    fmf.matched_filter(tp, mv, w, d, 1, check_zeros="first")
+    assert "correlation computations were skipped on the 0-th template" in capsys.readouterr().out
+
+
+def test_large_shape_properties():
+    """A BASELINE-sized slice (16 stations x 3 channels, L = 800, 20 min @ 100 Hz, 64 templates):
+    too big for the float64 brute force, checked through planted detections, |cc| <= sum w, chunk
+    additivity and agreement of the arithmetic variants with each other + oracle on a sub-window."""
+    T, S, C, L, N = 64, 16, 3, 800, 120000
+    tp, mv, w, d, planted = _synth.mf_case(T, S, C, L, N, seed=12)
+    precs = _precisions(L)
+    res = {p: fmf.matched_filter(tp, mv, w, d, 1, precision=p, check_zeros=False) for p in precs}
+    ref = res["fp32"]
+    for t, i0 in planted.items():
+        assert ref[t].argmax() == i0 and abs(ref[t, i0] - 1.0) < 1e-5
+    assert np.abs(ref).max() <= 1.0 + 1e-5
+    for p in precs[1:]:
+        assert np.abs(res[p] - ref).max() < _tol(p), p
+    sub = cpu.matched_filter(tp[:4], mv[:4], w[:4], d, 1)
+    assert np.abs(ref[:4] - sub).max() < 2e-6
