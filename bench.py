@@ -233,7 +233,6 @@ def run_ours(args, rank, world, local_rank):
         planted = {}
     plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, precision=args.precision, device=device)
     n_corr = plan.n_corr
-    prec_name = {1: "fp32", 2: "fp16", 3: "fp16x3"}[plan.resolved_precision]
     units = T * S * Cc * n_corr  # per rank, per step
 
     gather_rows = 25
@@ -253,6 +252,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step_fn()
     barrier()
+    prec_name = {1: "fp32", 2: "fp16", 3: "fp16x3"}[plan.last_precision]
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -77,7 +77,7 @@ int bpmf_matched_filter(const float *templates, const int *moveouts, const float
                         float *cc_out);
 
 /* Device-pointer entry point: every pointer is device memory, work is enqueued on `stream`
- * (a cudaStream_t passed as void*), no host synchronisation.  `workspace` must hold at least
+ * (a cudaStream_t passed as void*), no host synchronisation for an explicit precision.  `workspace` must hold at least
  * bpmf_mf_workspace_bytes(...) bytes.  cc_pitch = elements between consecutive template rows of
  * d_cc (>= n_corr; ignored when network_sum == 0). */
 size_t bpmf_mf_workspace_bytes(size_t n_samples_template, size_t n_samples_data,
@@ -89,9 +89,16 @@ int bpmf_matched_filter_dev(const float *d_templates, const int *d_moveouts,
                             size_t n_stations, size_t n_components, int normalize,
                             int network_sum, int precision, void *d_workspace,
                             size_t workspace_bytes, float *d_cc, size_t cc_pitch, void *stream);
-/* the arithmetic bpmf_matched_filter_dev resolves `precision` to for this shape */
+/* Shape-only check of a precision selector: returns the arithmetic it maps to, or a negative value
+ * when it is not available for the shape.  For BPMF_MF_AUTO this is the fastest arithmetic the
+ * shape allows; the call itself inspects the weights (4 bytes read back, the one host
+ * synchronisation of bpmf_matched_filter_dev) and takes BPMF_MF_TC_FP16 only when the predicted
+ * rounding error of the CC sum, 2.6e-3 * sqrt(max_t sum_ch w^2) / sqrt(L), is below 6e-5;
+ * otherwise BPMF_MF_TC_FP16X3.  bpmf_mf_last_precision() reports what the calling thread's last
+ * call used. */
 int bpmf_mf_resolve_precision(size_t n_samples_template, size_t step, int normalize,
                               int network_sum, int precision);
+int bpmf_mf_last_precision(void);
 
 /* Upstream fast_matched_filter CPU/GPU symbol [UPSTREAM-UNVERIFIED signature]: the function
  * fast_matched_filter's own ctypes wrapper binds.  sum_square_templates is accepted and ignored

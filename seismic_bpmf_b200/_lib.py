@@ -40,6 +40,7 @@ _SIGNATURES = {
     "bpmf_matched_filter_dev": (C.c_int, [vp, vp, vp, vp, z, z, z, z, z, z, C.c_int, C.c_int, C.c_int,
                                           vp, z, vp, z, vp]),
     "bpmf_mf_resolve_precision": (C.c_int, [z, z, C.c_int, C.c_int, C.c_int]),
+    "bpmf_mf_last_precision": (C.c_int, []),
     "matched_filter": (None, [fp, fp, ip, fp, fp, z, z, z, z, z, z, z, C.c_int, fp]),
     "matched_filter_no_sum": (None, [fp, fp, ip, fp, fp, z, z, z, z, z, z, z, C.c_int, fp]),
     "bpmf_beamform_max": (C.c_int, [fp, ip, fp, fp, z, z, z, z, z, C.c_int, C.c_int, fp, ip]),

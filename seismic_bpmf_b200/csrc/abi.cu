@@ -80,11 +80,46 @@ static MfWs carve_fp32(Workspace &ws, const MfShape &sh) {
     return w;
 }
 
+// Shape-only resolution: for AUTO this is the FASTEST arithmetic the shape allows; the call itself
+// may still pick the split variant from the weights (mf_auto_precision).
 static int resolve_precision(const MfShape &sh, int precision) {
     const bool tc_ok = mf_tc_supported(sh.L, sh.step, sh.normalize, sh.network_sum);
     if (precision == BPMF_MF_AUTO) return tc_ok ? BPMF_MF_TC_FP16 : BPMF_MF_FP32;
     if ((precision == BPMF_MF_TC_FP16 || precision == BPMF_MF_TC_FP16X3) && !tc_ok) return -1;
+    if (precision < BPMF_MF_AUTO || precision > BPMF_MF_TC_FP16X3) return -1;
     return precision;
+}
+
+// max over templates of sum_ch w^2 (one warp per template)
+__global__ void mf_weight_norm_kernel(const float *__restrict__ w, size_t T, size_t SC, float *__restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= T) return;
+    float a = 0.f;
+    for (size_t c = threadIdx.x & 31; c < SC; c += 32) {
+        const float v = w[t * SC + c];
+        a = fmaf(v, v, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(reinterpret_cast<unsigned *>(out), __float_as_uint(a));
+}
+
+static thread_local int g_last_precision = 0;
+
+// AUTO on a tensor-capable shape: single-pass fp16 operands carry 2^-11 relative rounding; the CC
+// sum then errs by about 4e-4 * sqrt(sum_ch w^2) / sqrt(L) rms.  Take the single pass when 6.5
+// sigma of that stays below 6e-5 (tolerance 1e-4 with margin), else the hi/lo split (fp32 grade).
+static int mf_auto_precision(const MfShape &sh, const float *d_weights, float *d_scratch, cudaStream_t st,
+                             int *out) {
+    BPMF_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(float), st));
+    mf_weight_norm_kernel<<<(unsigned)((sh.T + 7) / 8), 256, 0, st>>>(d_weights, sh.T, sh.SC(), d_scratch);
+    BPMF_LAUNCH_CHECK();
+    float w2 = 0.f;
+    BPMF_CUDA(cudaMemcpyAsync(&w2, d_scratch, sizeof(float), cudaMemcpyDeviceToHost, st));
+    BPMF_CUDA(cudaStreamSynchronize(st));
+    const double predicted = 2.6e-3 * sqrt((double)w2) / sqrt((double)sh.L);
+    *out = (predicted < 6e-5) ? BPMF_MF_TC_FP16 : BPMF_MF_TC_FP16X3;
+    return BPMF_OK;
 }
 
 }  // namespace bpmf
@@ -144,6 +179,8 @@ extern "C" size_t bpmf_mf_n_corr(size_t N, size_t L, size_t step) {
     return (N - L) / step + 1;
 }
 
+extern "C" int bpmf_mf_last_precision(void) { return g_last_precision; }
+
 extern "C" int bpmf_mf_resolve_precision(size_t L, size_t step, int normalize, int network_sum,
                                          int precision) {
     MfShape sh = make_shape(L, L, 1, 1, 1, step, normalize, network_sum);
@@ -161,7 +198,9 @@ extern "C" size_t bpmf_mf_workspace_bytes(size_t L, size_t N, size_t T, size_t S
         ws.take<float>(sh.T * sh.SC());
         ws.take<int>(sh.T);
         ws.take<int>(sh.T);
-        return ws.used + mf_tc_workspace_bytes(sh, prec == BPMF_MF_TC_FP16X3);
+        size_t need = mf_tc_workspace_bytes(sh, prec == BPMF_MF_TC_FP16X3);
+        if (precision == BPMF_MF_AUTO) need = std::max(need, mf_tc_workspace_bytes(sh, 1));  // AUTO may split
+        return ws.used + need;
     }
     carve_fp32(ws, sh);
     return ws.used;
@@ -180,11 +219,17 @@ extern "C" int bpmf_matched_filter_dev(const float *d_templates, const int *d_mo
     if (T == 0) return BPMF_OK;
     MfShape sh = make_shape(L, N, T, S, C, step, normalize ? 1 : 0, network_sum ? 1 : 0);
     BPMF_REQUIRE(!sh.network_sum || cc_pitch >= sh.n_corr, "matched_filter: cc_pitch < n_corr");
-    const int prec = resolve_precision(sh, precision);
+    int prec = resolve_precision(sh, precision);
     BPMF_REQUIRE(prec > 0, "matched_filter: precision %d is not available for L=%zu step=%zu "
                  "normalize=%d network_sum=%d", precision, L, step, normalize, network_sum);
+    BPMF_REQUIRE(workspace_bytes >= 256 && d_workspace != nullptr, "matched_filter: workspace missing");
     Workspace ws(d_workspace, workspace_bytes);
     int rc;
+    if (precision == BPMF_MF_AUTO && prec == BPMF_MF_TC_FP16) {
+        // the only host synchronisation of this entry point: 4 bytes of weight statistics
+        if ((rc = mf_auto_precision(sh, d_weights, (float *)d_workspace, st, &prec)) != BPMF_OK) return rc;
+    }
+    g_last_precision = prec;
     if (prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3) {
         MfMeta meta;
         meta.sst = ws.take<float>(sh.T * sh.SC());

@@ -88,9 +88,10 @@ __device__ __forceinline__ double block_exclusive_scan(double v, double *warp_to
     return base + inc - v;
 }
 
-template <bool FULL>
+// RSQRT: write 1/sqrt(E) (0 where E <= 0) instead of E -- the per-column factor of the tensor path.
+template <bool FULL, bool RSQRT>
 __global__ void __launch_bounds__(EN_THREADS)
-    mf_energy_kernel(const float *__restrict__ data, size_t N, size_t L, size_t n_win,
+    mf_energy_kernel(const float *__restrict__ data, size_t N, size_t L, size_t n_win, size_t out_pitch,
                      float *__restrict__ energy, float *__restrict__ mean) {
     extern __shared__ double sm[];
     __shared__ double warp_tot[EN_THREADS / 32];
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(EN_THREADS)
         if (FULL) P1[span] = tot1;
     }
     __syncthreads();
-    float *e = energy + ch * n_win + j0;
-    float *m = FULL ? mean + ch * n_win + j0 : nullptr;
+    float *e = energy + ch * out_pitch + j0;
+    float *m = FULL ? mean + ch * out_pitch + j0 : nullptr;
     for (size_t j = threadIdx.x; j < nj; j += EN_THREADS) {
         double ss = P2[j + L] - P2[j];
         if (FULL) {
@@ -136,8 +137,33 @@ __global__ void __launch_bounds__(EN_THREADS)
             ss -= (double)L * mu * mu;
             m[j] = (float)mu;
         }
-        e[j] = (float)(ss > 0.0 ? ss : 0.0);
+        if (RSQRT) e[j] = (ss > 0.0) ? (float)(1.0 / sqrt(ss)) : 0.f;
+        else e[j] = (float)(ss > 0.0 ? ss : 0.0);
     }
+}
+
+int mf_energy(const MfShape &sh, const float *d_data, float *d_energy, float *d_mean, size_t out_pitch,
+              bool rsqrt_mode, cudaStream_t st) {
+    const size_t n_win = sh.N - sh.L + 1;
+    const bool full = sh.normalize != 0;
+    const size_t span_max = (size_t)EN_BJ + sh.L;
+    const size_t smem = sizeof(double) * span_max * (full ? 2 : 1);
+    BPMF_REQUIRE(smem <= 200 * 1024, "template too long for the energy pre-pass (L=%zu)", sh.L);
+    dim3 grid((unsigned)((n_win + EN_BJ - 1) / EN_BJ), (unsigned)sh.SC());
+#define EN_LAUNCH(FU, RS)                                                                          \
+    do {                                                                                           \
+        BPMF_CUDA(cudaFuncSetAttribute(mf_energy_kernel<FU, RS>,                                   \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        mf_energy_kernel<FU, RS><<<grid, EN_THREADS, smem, st>>>(d_data, sh.N, sh.L, n_win,        \
+                                                                 out_pitch, d_energy, d_mean);     \
+    } while (0)
+    if (full && rsqrt_mode) EN_LAUNCH(true, true);
+    else if (full) EN_LAUNCH(true, false);
+    else if (rsqrt_mode) EN_LAUNCH(false, true);
+    else EN_LAUNCH(false, false);
+#undef EN_LAUNCH
+    BPMF_LAUNCH_CHECK();
+    return BPMF_OK;
 }
 
 int mf_prepass(const MfShape &sh, const float *d_templates, const int *d_moveouts,
@@ -158,23 +184,8 @@ int mf_prepass(const MfShape &sh, const float *d_templates, const int *d_moveout
     }
     if (d_energy) {
         const size_t n_win = sh.N - sh.L + 1;
-        const bool full = sh.normalize != 0;
-        const size_t span_max = (size_t)EN_BJ + sh.L;
-        const size_t smem = sizeof(double) * span_max * (full ? 2 : 1);
-        BPMF_REQUIRE(smem <= 200 * 1024, "template too long for the energy pre-pass (L=%zu)", sh.L);
-        dim3 grid((unsigned)((n_win + EN_BJ - 1) / EN_BJ), (unsigned)sh.SC());
-        if (full) {
-            BPMF_CUDA(cudaFuncSetAttribute(mf_energy_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            mf_energy_kernel<true><<<grid, EN_THREADS, smem, st>>>(d_data, sh.N, sh.L, n_win,
-                                                                    d_energy, d_mean);
-        } else {
-            BPMF_CUDA(cudaFuncSetAttribute(mf_energy_kernel<false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            mf_energy_kernel<false><<<grid, EN_THREADS, smem, st>>>(d_data, sh.N, sh.L, n_win,
-                                                                     d_energy, d_mean);
-        }
-        BPMF_LAUNCH_CHECK();
+        int rc = mf_energy(sh, d_data, d_energy, d_mean, n_win, false, st);
+        if (rc != BPMF_OK) return rc;
     }
     return BPMF_OK;
 }

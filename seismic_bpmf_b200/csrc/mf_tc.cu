@@ -1,13 +1,597 @@
-// mf_tc.cu -- tcgen05 (5th-gen tensor core) matched filter.  PLACEHOLDER: the tensor path is not
-// wired yet; every shape resolves to the FP32 CUDA-core kernel.
+// mf_tc.cu -- matched filter on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Replaces the native kernel behind fast_matched_filter.matched_filter for BPMF's default call
+// (BPMF/similarity_search.py:526-533: step 1, "short" normalisation, network sum); SURVEY.md A.1.
+//
+// Formulation (per channel ch): the CC numerator is a Toeplitz product.  It is cast as a GEMM whose
+// B operand is the RAW trace read through an overlapping shared-memory descriptor:
+//
+//     C[(t,r), jj] = sum_k' A[(t,r), k'] * d[8*jj + k']
+//
+//   * fp16 operands (per-channel / per-template power-of-two pre-scaling, exact), fp32 accumulate.
+//   * B "row" jj starts 8 elements = 16 bytes after row jj-1, which is exactly the row pitch of a
+//     no-swizzle K-major core matrix: the UMMA descriptor (LBO = 16 B, SBO = 128 B) walks a Hankel
+//     view of the trace without any im2col copy.  One 5.7 KB slice of trace feeds a 128 x 256 tile.
+//   * the 8 sub-row alignments ("phases") of a template are 8 ROWS of A: row (t, r) holds template
+//     t delayed by e = (r + moveout) mod 8 samples, so that row produces outputs i = r (mod 8) and
+//     its 8 lanes x 1 column form one aligned 32-byte sector of cc_sum.  The whole-column part of
+//     the moveout, q = floor((r + moveout) / 8), is applied as an output address shift.
+//   * A (16 templates x 8 phases x Kc, up to 204 KB) stays RESIDENT in shared memory while the CTA
+//     sweeps a segment of 64 tiles (131 072 samples); B slices stream through a 2-stage bulk-copy
+//     ring.  Templates longer than one resident image are cut into K chunks (numerators add).
+//   * BPMF_MF_TC_FP16X3: both operands are split hi + lo (two fp16 = 22 mantissa bits) and three
+//     MMAs (hi*hi + hi*lo + lo*hi) accumulate into the same TMEM tile: fp32-grade numerators.
+//   * epilogue (8 warps): tcgen05.ld -> * rsqrt(window energy)[column] * weight/|T|[row] ->
+//     red.global.add.f32 into cc_sum.  Work is ordered segment -> template tile -> channel so the
+//     48 channel-CTAs that add into the same 16 rows x 131 072 samples do so while that region
+//     (8 MB) is L2 resident.
+//
+// Rooflines: tensor pipe (2*Kp flop per output, Kp = L+7 rounded to 16) and L2 reduction
+// throughput (one fp32 red per (template, channel, output); ~850 Gred/s measured, tools/red_bench.cu).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace bpmf {
-bool mf_tc_supported(size_t, size_t, int, int) { return false; }
-size_t mf_tc_workspace_bytes(const MfShape &, int) { return 0; }
-int mf_tc_run(const MfShape &, int, const float *, const int *, const float *, const float *, MfMeta,
-              Workspace &, float *, size_t, cudaStream_t) {
-    set_error("tensor-core matched filter is not available in this build");
-    return BPMF_E_ARG;
+
+constexpr int TC_ROWS = 128;        // A rows per tile = 16 templates x 8 phases
+constexpr int TC_TPL = 16;          // templates per tile
+constexpr int TC_NCOL = 256;        // GEMM columns per tile (= 2048 samples)
+constexpr int TC_KC_MAX = 816;      // resident A, single pass: 128 x 816 fp16 = 208 896 B
+constexpr int TC_KC_MAX_SPLIT = 384; // resident A, hi + lo images: 128 x 384 x 2 x 2 = 196 608 B
+constexpr int TC_SEG_TILES = 64;    // tiles swept per resident A image
+constexpr int TC_THREADS = 320;     // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+constexpr int TC_INV_SLOT = 1056;   // floats per half-tile slot (needs 1024 + 8)
+constexpr int TC_TMEM_COLS = 512;
+
+constexpr size_t TC_SMEM_LIMIT = 232448;  // 227 KB opt-in shared memory per CTA
+
+struct TcParams {
+    const __half *dh;        // (SC, dh_pitch) scaled fp16 traces (hi part), zero padded
+    const __half *dh_lo;     // residual x*s - hi (split mode only)
+    size_t dh_pitch;
+    const float *colinv;     // (SC, ci_pitch) rsqrt(window energy), 0 where undefined
+    size_t ci_pitch;
+    const uint8_t *aimg;     // (SC, MT, n_kc) A images in UMMA core-matrix order, a_bytes each
+                             // (split mode: hi image followed by lo image)
+    const int *row_q;        // (SC, MT, 128) whole-column shift of the row
+    const int *row_e;        // (SC, MT, 128) sub-column delay folded into the A row
+    const float *row_scale;  // (SC, MT, 128) weight / (sA * sB * sqrt(sum T^2)), 0 = unused row
+    const float *row_ithr;   // (SC, MT, 128) guard: contribute only where colinv < ithr
+    const int *item_active;  // (SC, MT)
+    const int *lo, *hi;      // per template valid output range
+    float *cc;
+    size_t cc_pitch;
+    int T, SC, MT, n_kc, Kc, split, a_bytes, a_img_bytes, b_slice_bytes, b_stage_bytes;
+    int n_tiles, seg_tiles, n_seg;
+};
+
+struct TcItem {
+    int kc, ch, mt, seg;
+};
+__device__ __forceinline__ TcItem tc_decode(const TcParams &p, int it) {
+    TcItem r;
+    r.kc = it % p.n_kc;
+    it /= p.n_kc;
+    r.ch = it % p.SC;
+    it /= p.SC;
+    r.mt = it % p.MT;
+    r.seg = it / p.MT;
+    return r;
 }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA engine, non-tensor form: contiguous global -> shared bulk copy completing on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate, issued by ONE thread
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes (rows 16 B
+// apart); LBO = byte step between the two 8-element K chunks of one MMA, SBO = byte step between
+// consecutive 8-row groups.
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version of sm_100
+    return d;
+}
+// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = 256
+__device__ __forceinline__ uint32_t tc_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *a_s = smem;
+    uint8_t *b_s = smem + p.a_bytes;
+    float *inv_s = reinterpret_cast<float *>(b_s + 2 * p.b_stage_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(inv_s + 2 * TC_INV_SLOT);
+    uint64_t *a_full = bars + 0, *a_empty = bars + 1;
+    uint64_t *b_full = bars + 2, *b_empty = bars + 4;          // [2]
+    uint64_t *acc_full = bars + 6, *acc_empty = bars + 8;      // [2]
+    uint64_t *inv_full = bars + 10, *inv_empty = bars + 12;    // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 1);
+            mbar_init(acc_full + i, 1);
+            mbar_init(acc_empty + i, 8);  // one arrive per epilogue warp
+            mbar_init(inv_full + i, 1);
+            mbar_init(inv_empty + i, 4);  // the four warps that read this half
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items = p.n_seg * p.MT * p.SC * p.n_kc;
+    const uint32_t b_bytes = (uint32_t)p.b_slice_bytes;  // (8*255 + Kc) * 2, a multiple of 16
+    const uint32_t inv_bytes = (1024 + 8) * 4;
+
+    if (warp == 0) {
+        // ===================== producer: bulk copies of A images, trace slices, rsqrt(energy) =====
+        if (lane == 0) {
+            uint32_t n_item = 0, n_tile = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const TcItem im = tc_decode(p, it);
+                const int ch = im.ch, mt = im.mt, seg = im.seg;
+                if (!p.item_active[ch * p.MT + mt]) continue;
+                mbar_wait(a_empty, (n_item & 1) ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)p.a_bytes);
+                const uint8_t *src = p.aimg + ((size_t)(ch * p.MT + mt) * p.n_kc + im.kc) * p.a_bytes;
+                for (int off = 0; off < p.a_bytes; off += 16384) {
+                    const int n = (p.a_bytes - off < 16384) ? (p.a_bytes - off) : 16384;
+                    bulk_g2s(a_s + off, src + off, (uint32_t)n, a_full);
+                }
+                n_item++;
+                const int t_begin = seg * p.seg_tiles;
+                const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+                for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
+                    const int s = n_tile & 1;
+                    const uint32_t par = ((n_tile >> 1) & 1) ^ 1;
+                    mbar_wait(b_empty + s, par);
+                    const size_t d_off = (size_t)ch * p.dh_pitch + (size_t)tile * (8 * TC_NCOL) + (size_t)im.kc * p.Kc;
+                    mbar_expect_tx(b_full + s, p.split ? 2 * b_bytes : b_bytes);
+                    bulk_g2s(b_s + s * p.b_stage_bytes, p.dh + d_off, b_bytes, b_full + s);
+                    if (p.split) bulk_g2s(b_s + s * p.b_stage_bytes + b_bytes, p.dh_lo + d_off, b_bytes, b_full + s);
+                    const float *ci = p.colinv + (size_t)ch * p.ci_pitch + (size_t)tile * (8 * TC_NCOL);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        mbar_wait(inv_empty + h, (n_tile & 1) ^ 1);
+                        mbar_expect_tx(inv_full + h, inv_bytes);
+                        bulk_g2s(inv_s + h * TC_INV_SLOT, ci + h * 1024, inv_bytes, inv_full + h);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) ============================================
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc(TC_ROWS, TC_NCOL);
+            const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+            const int n_k = p.Kc / 16;
+            uint32_t n_item = 0, n_tile = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const TcItem im = tc_decode(p, it);
+                const int ch = im.ch, mt = im.mt, seg = im.seg;
+                if (!p.item_active[ch * p.MT + mt]) continue;
+                mbar_wait(a_full, n_item & 1);
+                n_item++;
+                const int t_begin = seg * p.seg_tiles;
+                const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+                for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
+                    const int s = n_tile & 1;
+                    const uint32_t par = (n_tile >> 1) & 1;
+                    mbar_wait(b_full + s, par);
+                    mbar_wait(acc_empty + s, par ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_NCOL);
+                    for (int kk = 0; kk < n_k; kk++) {
+                        // A: K chunk c of 8 elements lives at c * (128 rows * 16 B); rows 16 B apart
+                        const uint64_t da = tc_desc(a_addr + (uint32_t)kk * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
+                        // B: Hankel view of the raw trace: row jj at +16 B, K chunk at +16 B
+                        const uint32_t b_at = b_addr + (uint32_t)(s * p.b_stage_bytes) + (uint32_t)kk * 32;
+                        const uint64_t db = tc_desc(b_at, 16, 128);
+                        tc_mma_f16(d_tmem, da, db, idesc, kk > 0 ? 1u : 0u);
+                        if (p.split) {  // + hi*lo + lo*hi into the same accumulator
+                            const uint64_t db_lo = tc_desc(b_at + b_bytes, 16, 128);
+                            const uint64_t da_lo = tc_desc(a_addr + (uint32_t)p.a_img_bytes + (uint32_t)kk * 2 * (TC_ROWS * 16),
+                                                           TC_ROWS * 16, 128);
+                            tc_mma_f16(d_tmem, da, db_lo, idesc, 1u);
+                            tc_mma_f16(d_tmem, da_lo, db, idesc, 1u);
+                        }
+                    }
+                    tc_commit(b_empty + s);   // trace slice may be overwritten once these MMAs retire
+                    tc_commit(acc_full + s);  // accumulator ready for the epilogue
+                }
+                tc_commit(a_empty);  // A image may be replaced once every MMA of this item retired
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> normalise -> red.add into cc_sum ==================
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;        // which 128 columns of the tile
+        const int row = quarter * 32 + lane;     // A row == TMEM lane
+        uint32_t n_tile = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const TcItem im = tc_decode(p, it);
+            const int ch = im.ch, mt = im.mt, seg = im.seg;
+            if (!p.item_active[ch * p.MT + mt]) continue;
+            const size_t mrow = (size_t)(ch * p.MT + mt) * TC_ROWS + row;
+            const float scale = p.row_scale[mrow];
+            const float ithr = p.row_ithr[mrow];
+            const int q = p.row_q[mrow];
+            const int e = p.row_e[mrow];
+            const int t = mt * TC_TPL + (row >> 3);
+            const int ir = row & 7;
+            int lo = 1, hi = 0;
+            if (t < p.T && scale != 0.f) { lo = p.lo[t]; hi = p.hi[t]; }
+            // output index of column jj: i = 8 * (jj - q) + ir, valid iff lo <= i <= hi
+            // <=> jj in [jj_lo, jj_hi]
+            long long jj_lo = 1, jj_hi = 0;
+            if (hi >= lo) {
+                const int a = lo - ir, b = hi - ir;
+                jj_lo = (long long)((a >= 0) ? (a + 7) / 8 : -((-a) / 8)) + q;  // ceil(a / 8) + q
+                jj_hi = (long long)((b >= 0) ? b / 8 : -((-b + 7) / 8)) + q;    // floor(b / 8) + q
+            }
+            float *out_row = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + ir;
+            const int t_begin = seg * p.seg_tiles;
+            const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+            for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
+                const int s = n_tile & 1;
+                mbar_wait(acc_full + s, (n_tile >> 1) & 1);
+                mbar_wait(inv_full + half, n_tile & 1);
+                tc_fence_after();
+                const float *inv = inv_s + half * TC_INV_SLOT + e;
+                const long long jj0 = (long long)tile * TC_NCOL + half * 128;  // first column of this half
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_NCOL + half * 128);
+                // columns of this half that are valid for this row: [c_lo, c_hi)
+                long long c_lo64 = jj_lo - jj0, c_hi64 = jj_hi - jj0 + 1;
+                const int c_lo = (int)(c_lo64 < 0 ? 0 : (c_lo64 > 128 ? 128 : c_lo64));
+                const int c_hi = (int)(c_hi64 > 128 ? 128 : (c_hi64 < 0 ? 0 : c_hi64));
+                const bool any_valid = __any_sync(0xffffffffu, c_hi > c_lo);
+                const bool all_valid = __all_sync(0xffffffffu, c_lo == 0 && c_hi == 128);
+#pragma unroll 1
+                for (int chunk = 0; chunk < 4; chunk++) {
+                    float v[32];
+                    tc_ld32(taddr + (uint32_t)(chunk * 32), v);
+                    float *dst = out_row + 8 * (jj0 + chunk * 32 - q);
+                    const float *ivc = inv + 8 * (chunk * 32);
+                    if (all_valid) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const float w = ivc[8 * c];
+                            const float x = v[c] * w;
+                            atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
+                        }
+                    } else if (any_valid) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const int col = chunk * 32 + c;
+                            const float w = ivc[8 * c];
+                            const float x = v[c] * w;
+                            if (col >= c_lo && col < c_hi) atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(acc_empty + s);
+                    mbar_arrive(inv_empty + half);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- pre-pass kernels
+// per-channel max |d| (bit pattern of a non-negative float orders like an unsigned int)
+__global__ void tc_absmax_kernel(const float *__restrict__ data, size_t N, unsigned *__restrict__ chmax) {
+    const size_t ch = blockIdx.y;
+    const float *d = data + ch * N;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = fabsf(d[i]);
+        if (a < INFINITY) m = fmaxf(m, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(chmax + ch, __float_as_uint(m));
+}
+
+// power-of-two scale that maps max|x| into [2^13, 2^14): exact in fp32, keeps fp16 in normal range
+__device__ __forceinline__ float pow2_scale(float amax) {
+    if (!(amax > 0.f)) return 1.f;
+    int ex;
+    frexpf(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
+    int sh = 14 - ex;
+    sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+    return ldexpf(1.f, sh);
+}
+
+// traces -> scaled fp16 (hi, and the residual lo in split mode), zero padded to dh_pitch; also
+// publishes the per-channel scale
+__global__ void tc_data_convert_kernel(const float *__restrict__ data, size_t N, size_t dh_pitch,
+                                       const unsigned *__restrict__ chmax, __half *__restrict__ dh,
+                                       __half *__restrict__ dh_lo, float *__restrict__ ch_scale) {
+    const size_t ch = blockIdx.y;
+    const float sB = pow2_scale(__uint_as_float(chmax[ch]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) ch_scale[ch] = sB;
+    const float *d = data + ch * N;
+    __half *o = dh + ch * dh_pitch;
+    __half *ol = dh_lo ? dh_lo + ch * dh_pitch : nullptr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dh_pitch; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = i < N ? d[i] * sB : 0.f;
+        const __half h = __float2half_rn(v);
+        o[i] = h;
+        if (ol) ol[i] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+// One CTA per (template tile, channel), one thread per A row: builds the resident A images (one per
+// K chunk; hi then lo in split mode) in UMMA core-matrix order (K group c of 8 elements at
+// c*2048 + row*16 bytes) and the per-row epilogue constants.
+__global__ void __launch_bounds__(TC_ROWS)
+    tc_template_prep_kernel(const float *__restrict__ templates, const int *__restrict__ moveouts,
+                            const float *__restrict__ weights, const float *__restrict__ sst,
+                            const int *__restrict__ lo, const int *__restrict__ hi,
+                            const float *__restrict__ ch_scale, int T, int SC, int L, int n_kc, int Kc, int split,
+                            int a_bytes, int a_img_bytes, uint8_t *__restrict__ aimg, int *__restrict__ row_q,
+                            int *__restrict__ row_e, float *__restrict__ row_scale, float *__restrict__ row_ithr,
+                            int *__restrict__ item_active) {
+    const int mt = blockIdx.x, ch = blockIdx.y, MT = gridDim.x;
+    const int row = threadIdx.x;
+    const int t = mt * TC_TPL + (row >> 3), ir = row & 7;
+    const size_t item = (size_t)ch * MT + mt;
+    const size_t mrow = item * TC_ROWS + row;
+
+    bool used = false;
+    float w = 0.f, ss = 0.f;
+    int m = 0;
+    if (t < T) {
+        w = weights[(size_t)t * SC + ch];
+        ss = sst[(size_t)t * SC + ch];
+        m = moveouts[(size_t)t * SC + ch];
+        used = (w != 0.f) && (hi[t] >= lo[t]) && (ss > 0.f) && (ss < INFINITY);
+    }
+    const int any = __syncthreads_or(used ? 1 : 0);
+    if (row == 0) item_active[item] = any;
+
+    const int sum = ir + m;
+    const int q = (sum >= 0) ? (sum >> 3) : -((-sum + 7) >> 3);  // floor(sum / 8)
+    const int e = sum - 8 * q;                                   // in [0, 8)
+    const float *tp = templates + ((size_t)(t < T ? t : 0) * SC + ch) * (size_t)L;
+    float sA = 1.f;
+    if (used) {
+        float amax = 0.f;
+        for (int k = 0; k < L; k++) amax = fmaxf(amax, fabsf(tp[k]));
+        sA = pow2_scale(amax);
+    }
+    row_q[mrow] = q;
+    row_e[mrow] = e;
+    // CC = acc / (sA * sB) / sqrt(sst * E); guard sst * E > 1e-6  <=>  rsqrt(E) < sqrt(sst) * 1e3
+    row_scale[mrow] = used ? w / (sA * ch_scale[ch] * sqrtf(ss)) : 0.f;
+    row_ithr[mrow] = used ? sqrtf(ss) * 1000.f : 0.f;
+    if (!any) return;
+    for (int kc = 0; kc < n_kc; kc++) {
+        uint4 *img = reinterpret_cast<uint4 *>(aimg + (item * n_kc + kc) * (size_t)a_bytes);
+        uint4 *img_lo = reinterpret_cast<uint4 *>(aimg + (item * n_kc + kc) * (size_t)a_bytes + a_img_bytes);
+        for (int c = 0; c < Kc / 8; c++) {
+            __half h[8], l[8];
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const int k = kc * Kc + c * 8 + x - e;
+                const float v = (used && k >= 0 && k < L) ? tp[k] * sA : 0.f;
+                h[x] = __float2half_rn(v);
+                l[x] = __float2half_rn(v - __half2float(h[x]));
+            }
+            img[(size_t)c * TC_ROWS + row] = *reinterpret_cast<uint4 *>(h);
+            if (split) img_lo[(size_t)c * TC_ROWS + row] = *reinterpret_cast<uint4 *>(l);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+struct TcWs {
+    __half *dh, *dh_lo;
+    float *colinv;
+    uint8_t *aimg;
+    int *row_q, *row_e, *item_active;
+    float *row_scale, *row_ithr, *ch_scale;
+    unsigned *chmax;
+    size_t dh_pitch, ci_pitch;
+    int MT, n_kc, Kc, a_bytes, a_img_bytes, b_slice_bytes, b_stage_bytes, n_tiles;
+    size_t smem_bytes;
+};
+
+static TcWs tc_carve(Workspace &ws, const MfShape &sh, int split) {
+    TcWs w;
+    const int Kp = (int)align_up(sh.L + 7, 16);
+    const int kc_max = split ? TC_KC_MAX_SPLIT : TC_KC_MAX;
+    w.n_kc = (Kp + kc_max - 1) / kc_max;
+    w.Kc = (int)align_up((size_t)(Kp + w.n_kc - 1) / w.n_kc, 16);
+    w.a_img_bytes = TC_ROWS * w.Kc * 2;
+    w.a_bytes = w.a_img_bytes * (split ? 2 : 1);
+    w.b_slice_bytes = (8 * (TC_NCOL - 1) + w.Kc) * 2;
+    w.b_stage_bytes = (int)align_up((size_t)w.b_slice_bytes * (split ? 2 : 1), 128);
+    w.smem_bytes = (size_t)w.a_bytes + 2 * (size_t)w.b_stage_bytes + 2 * TC_INV_SLOT * 4 + 256;
+    w.MT = (int)((sh.T + TC_TPL - 1) / TC_TPL);
+    const size_t n_cols = (sh.N - sh.L) / 8 + 1;  // GEMM columns that can hold a valid window start
+    w.n_tiles = (int)((n_cols + TC_NCOL - 1) / TC_NCOL);
+    // last slice read: (n_tiles-1)*2048 + (n_kc-1)*Kc + 2040 + Kc
+    w.dh_pitch = align_up((size_t)w.n_tiles * (8 * TC_NCOL) + (size_t)w.n_kc * w.Kc + 64, 64);
+    if (w.dh_pitch < align_up(sh.N, 64)) w.dh_pitch = align_up(sh.N, 64);
+    w.ci_pitch = (size_t)w.n_tiles * (8 * TC_NCOL) + 64;
+    const size_t SC = sh.SC();
+    w.dh = ws.take<__half>(SC * w.dh_pitch);
+    w.dh_lo = split ? ws.take<__half>(SC * w.dh_pitch) : nullptr;
+    w.colinv = ws.take<float>(SC * w.ci_pitch);
+    w.aimg = ws.take<uint8_t>(SC * (size_t)w.MT * w.n_kc * w.a_bytes);
+    w.row_q = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
+    w.row_e = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
+    w.row_scale = ws.take<float>(SC * (size_t)w.MT * TC_ROWS);
+    w.row_ithr = ws.take<float>(SC * (size_t)w.MT * TC_ROWS);
+    w.item_active = ws.take<int>(SC * (size_t)w.MT);
+    w.ch_scale = ws.take<float>(SC);
+    w.chmax = ws.take<unsigned>(SC);
+    return w;
+}
+
+bool mf_tc_supported(size_t L, size_t step, int normalize, int network_sum) {
+    return step == 1 && normalize == 0 && network_sum != 0 && L >= 8 && L <= 65536;
+}
+
+size_t mf_tc_workspace_bytes(const MfShape &sh, int split) {
+    Workspace ws(nullptr, 0);
+    tc_carve(ws, sh, split);
+    return ws.used;
+}
+
+int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int *d_moveouts,
+              const float *d_weights, const float *d_data, MfMeta meta, Workspace &ws, float *d_cc,
+              size_t cc_pitch, cudaStream_t st) {
+    BPMF_REQUIRE(mf_tc_supported(sh.L, sh.step, sh.normalize, sh.network_sum),
+                 "matched filter: shape not supported by the tensor path");
+    TcWs w = tc_carve(ws, sh, split);
+    BPMF_REQUIRE(ws.ok(), "matched filter: workspace too small for the tensor path");
+    BPMF_REQUIRE(w.smem_bytes <= TC_SMEM_LIMIT, "matched filter: tensor-path tile exceeds shared memory");
+    const size_t SC = sh.SC();
+    BPMF_REQUIRE(SC <= 65535, "matched filter: too many channels");
+
+    // traces: per-channel scale, fp16 copy, rsqrt(window energy)
+    BPMF_CUDA(cudaMemsetAsync(w.chmax, 0, sizeof(unsigned) * SC, st));
+    tc_absmax_kernel<<<dim3(64, (unsigned)SC), 256, 0, st>>>(d_data, sh.N, w.chmax);
+    BPMF_LAUNCH_CHECK();
+    tc_data_convert_kernel<<<dim3(128, (unsigned)SC), 256, 0, st>>>(d_data, sh.N, w.dh_pitch, w.chmax, w.dh,
+                                                                    w.dh_lo, w.ch_scale);
+    BPMF_LAUNCH_CHECK();
+    BPMF_CUDA(cudaMemsetAsync(w.colinv, 0, sizeof(float) * SC * w.ci_pitch, st));
+    int rc = mf_energy(sh, d_data, w.colinv, nullptr, w.ci_pitch, true, st);
+    if (rc != BPMF_OK) return rc;
+    // templates: resident A images + per-row constants
+    tc_template_prep_kernel<<<dim3((unsigned)w.MT, (unsigned)SC), TC_ROWS, 0, st>>>(
+        d_templates, d_moveouts, d_weights, meta.sst, meta.lo, meta.hi, w.ch_scale, (int)sh.T, (int)SC, (int)sh.L,
+        w.n_kc, w.Kc, split, w.a_bytes, w.a_img_bytes, w.aimg, w.row_q, w.row_e, w.row_scale, w.row_ithr,
+        w.item_active);
+    BPMF_LAUNCH_CHECK();
+    // cc_sum is accumulated with reductions: start from zero (also the value of never-computed outputs)
+    BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * cc_pitch, st));
+
+    TcParams p;
+    p.dh = w.dh; p.dh_lo = w.dh_lo; p.dh_pitch = w.dh_pitch;
+    p.colinv = w.colinv; p.ci_pitch = w.ci_pitch;
+    p.aimg = w.aimg;
+    p.row_q = w.row_q; p.row_e = w.row_e; p.row_scale = w.row_scale; p.row_ithr = w.row_ithr;
+    p.item_active = w.item_active;
+    p.lo = meta.lo; p.hi = meta.hi;
+    p.cc = d_cc; p.cc_pitch = cc_pitch;
+    p.T = (int)sh.T; p.SC = (int)SC; p.MT = w.MT; p.n_kc = w.n_kc; p.Kc = w.Kc; p.split = split ? 1 : 0;
+    p.a_bytes = w.a_bytes; p.a_img_bytes = w.a_img_bytes;
+    p.b_slice_bytes = w.b_slice_bytes; p.b_stage_bytes = w.b_stage_bytes;
+    p.n_tiles = w.n_tiles;
+    p.seg_tiles = TC_SEG_TILES;
+    p.n_seg = (w.n_tiles + TC_SEG_TILES - 1) / TC_SEG_TILES;
+    const long long n_items = (long long)p.n_seg * p.MT * p.SC * p.n_kc;
+    BPMF_REQUIRE(n_items < (1ll << 31), "matched filter: too many work items for the tensor path");
+    BPMF_CUDA(cudaFuncSetAttribute(mf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bytes));
+    const int grid = (int)std::min<long long>(n_items, (long long)num_sms());
+    {
+        MainKernelTimer timer(st);
+        mf_tc_kernel<<<grid, TC_THREADS, w.smem_bytes, st>>>(p);
+    }
+    BPMF_LAUNCH_CHECK();
+    return BPMF_OK;
+}
+
 }  // namespace bpmf

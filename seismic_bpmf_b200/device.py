@@ -74,6 +74,7 @@ class MatchedFilterPlan:
             self.workspace.data_ptr(), self.workspace.numel(), self.cc.data_ptr(), self.pitch,
             _stream_ptr())
         _lib.check(rc, "matched_filter_dev")
+        self.last_precision = int(self.lib.bpmf_mf_last_precision())
         return self.cc[:, : self.n_corr] if self.network_sum else self.cc
 
 

@@ -14,7 +14,7 @@ TOL = 1e-4
 
 def _precisions(L, step=1, normalize="short", network_sum=True):
     lib = _lib.load()
-    out = ["fp32"]
+    out = ["fp32", "auto"]
     for name in ("fp16", "fp16x3"):
         if lib.bpmf_mf_resolve_precision(L, step, 1 if normalize == "full" else 0, 1 if network_sum else 0,
                                          _lib.PRECISIONS[name]) > 0:
@@ -22,8 +22,18 @@ def _precisions(L, step=1, normalize="short", network_sum=True):
     return out
 
 
-def _tol(prec):
-    return 2e-6 if prec in ("fp32", "fp16x3") else TOL
+def _tol(prec, L=800, w=None):
+    """fp32 and the hi/lo split are fp32-grade; "auto" must always meet the north-star 1e-4; an
+    explicit single-pass fp16 request is held to the documented error model
+    2.6e-3 * sqrt(max_t sum w^2) / sqrt(L) (include/bpmf_b200.h), which is what "auto" checks."""
+    if prec == "fp32":
+        return 2e-6
+    if prec == "fp16x3":
+        return 1e-5
+    if prec == "auto":
+        return TOL
+    w2 = 1.0 if w is None else float((np.asarray(w, np.float64) ** 2).sum(axis=(1, 2)).max())
+    return max(2e-5, 1.5 * 2.6e-3 * np.sqrt(w2) / np.sqrt(L))
 
 
 def test_cfg1_shape_vs_oracle():
@@ -35,10 +45,10 @@ def test_cfg1_shape_vs_oracle():
         assert got.shape == want.shape == (1, 180000 - 400 + 1)
         assert got.dtype == np.float32 and got.flags.writeable
         err = np.abs(got - want).max()
-        assert err < _tol(prec), (prec, err)
+        assert err < _tol(prec, 400, w), (prec, err)
         assert np.array_equal(got == 0, want == 0), prec
         for t, i0 in planted.items():
-            assert got[t].argmax() == i0 and abs(got[t, i0] - w[t].sum()) < _tol(prec) + 1e-6
+            assert got[t].argmax() == i0 and abs(got[t, i0] - w[t].sum()) < _tol(prec, 400, w) + 1e-6
 
 
 @pytest.mark.parametrize("T,S,C,L,N", [(7, 5, 3, 200, 30011), (33, 3, 2, 800, 20000), (2, 2, 1, 37, 4133),
@@ -49,7 +59,7 @@ def test_vs_oracle_shapes(T, S, C, L, N):
     for prec in _precisions(L):
         got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
         err = np.abs(got - want).max()
-        assert err < _tol(prec), (prec, err)
+        assert err < _tol(prec, L, w), (prec, err)
         assert np.array_equal(got == 0, want == 0), prec
 
 
@@ -58,7 +68,7 @@ def test_float64_brute_force_agreement():
     want = numpy_ref.matched_filter(tp, mv, w, d, 1)
     for prec in _precisions(128):
         got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
-        assert np.abs(got - want).max() < _tol(prec), prec
+        assert np.abs(got - want).max() < _tol(prec, 128, w), prec
 
 
 @pytest.mark.parametrize("step", [2, 3, 8, 25])
@@ -68,7 +78,7 @@ def test_step_is_a_subsampling(step):
     for prec in _precisions(100, step=step):
         got = fmf.matched_filter(tp, mv, w, d, step, precision=prec, check_zeros=False)
         assert got.shape == (4, (15000 - 100) // step + 1)
-        assert np.abs(got - base[:, ::step]).max() < _tol(prec), prec
+        assert np.abs(got - base[:, ::step]).max() < _tol(prec, 100, w), prec
     assert np.abs(fmf.matched_filter(tp, mv, w, d, step, precision="fp32", check_zeros=False) -
                   cpu.matched_filter(tp, mv, w, d, step)).max() < 2e-6
 
@@ -98,7 +108,7 @@ def test_network_sum_false_layout():
 def test_known_answers_and_invariances():
     tp, mv, w, d, planted = _synth.mf_case(6, 4, 3, 256, 40000, seed=8)
     for prec in _precisions(256):
-        tol = _tol(prec)
+        tol = _tol(prec, 256, w)
         cc = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
         assert np.isfinite(cc).all()
         for t, i0 in planted.items():
@@ -116,6 +126,7 @@ def test_known_answers_and_invariances():
 
 def test_bounds_negative_moveouts_and_zero_weight_channels():
     tp, mv, w, d, _ = _synth.mf_case(3, 3, 2, 80, 6000, seed=9, plant=False)
+    mv[0] = np.arange(6).reshape(3, 2) * 11
     mv[0, 0, 0], mv[0, 1, 1] = -53, 977
     mv[2] = -5
     w[1, 2, :] = 0
@@ -128,7 +139,7 @@ def test_bounds_negative_moveouts_and_zero_weight_channels():
         assert np.all(got[0, :53] == 0) and got[0, 53] != 0
         last = 6000 - 80 - 977
         assert got[0, last] != 0 and np.all(got[0, last + 1:] == 0)
-        assert np.abs(got - want).max() < _tol(prec)
+        assert np.abs(got - want).max() < _tol(prec, 80, w)
 
 
 def test_edge_shapes():
@@ -140,7 +151,7 @@ def test_edge_shapes():
     w = np.ones((2, 1, 1), np.float32)
     got = fmf.matched_filter(tp, mv, w, d, 1, check_zeros=False)
     assert got.shape == (2, 1)
-    assert np.abs(got - cpu.matched_filter(tp, mv, w, d, 1)).max() < 2e-6
+    assert np.abs(got - cpu.matched_filter(tp, mv, w, d, 1)).max() < 1e-5
     # all-zero weights for one template -> a zero row (BPMF skips them, similarity_search.py:510-512)
     w[1] = 0
     got = fmf.matched_filter(tp, mv, w, d, 1, check_zeros=False)
@@ -155,7 +166,7 @@ def test_edge_shapes():
     w3 = np.ones((2, 2, 3))
     got = fmf.matched_filter(tp3, mv2, w3, d3[:, :, ::1], 1, check_zeros=False)
     want = cpu.matched_filter(tp3, mv2, w3, d3, 1)
-    assert np.abs(got - want).max() < 2e-6
+    assert np.abs(got - want).max() < 2e-5  # un-normalised weights (sum = 6): auto takes the split path
     # tiny amplitudes collapse to exact zero through the stability guard
     got = fmf.matched_filter(tp3 * 1e-6, mv2, w3, d3 * 1e-6, 1, check_zeros=False)
     assert np.all(got == 0)
@@ -178,6 +189,29 @@ def test_upstream_symbol_and_check_zeros_message(capsys):
     assert "correlation computations were skipped on the 0-th template" in capsys.readouterr().out
 
 
+def test_auto_policy_and_long_templates():
+    """AUTO takes the single fp16 pass only when the error model allows it; templates longer than one
+    resident A image (L > 809) run as several K chunks."""
+    lib = _lib.load()
+    tp, mv, w, d, _ = _synth.mf_case(5, 8, 3, 800, 30000, seed=31)
+    want = cpu.matched_filter(tp, mv, w, d, 1)
+    got = fmf.matched_filter(tp, mv, w, d, 1, check_zeros=False)
+    assert lib.bpmf_mf_last_precision() == _lib.MF_TC_FP16  # 24 equal weights, L = 800
+    assert np.abs(got - want).max() < TOL
+    w1 = np.zeros_like(w)
+    w1[:, 0, 0] = 1.0  # a single channel carries the whole sum: single-pass error would be ~1e-4
+    got = fmf.matched_filter(tp, mv, w1, d, 1, check_zeros=False)
+    assert lib.bpmf_mf_last_precision() == _lib.MF_TC_FP16X3
+    assert np.abs(got - cpu.matched_filter(tp, mv, w1, d, 1)).max() < 1e-5
+    for L in (810, 1500, 2049):
+        tp, mv, w, d, _ = _synth.mf_case(3, 3, 2, L, 20000, seed=L)
+        want = cpu.matched_filter(tp, mv, w, d, 1)
+        for prec in ("fp16", "fp16x3"):
+            got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
+            assert np.abs(got - want).max() < _tol(prec, L, w), (L, prec)
+            assert np.array_equal(got == 0, want == 0)
+
+
 def test_large_shape_properties():
     """A BASELINE-sized slice (16 stations x 3 channels, L = 800, 20 min @ 100 Hz, 64 templates):
     too big for the float64 brute force, checked through planted detections, |cc| <= sum w, chunk
@@ -191,6 +225,6 @@ def test_large_shape_properties():
         assert ref[t].argmax() == i0 and abs(ref[t, i0] - 1.0) < 1e-5
     assert np.abs(ref).max() <= 1.0 + 1e-5
     for p in precs[1:]:
-        assert np.abs(res[p] - ref).max() < _tol(p), p
+        assert np.abs(res[p] - ref).max() < _tol(p, L, w), p
     sub = cpu.matched_filter(tp[:4], mv[:4], w[:4], d, 1)
     assert np.abs(ref[:4] - sub).max() < 2e-6
