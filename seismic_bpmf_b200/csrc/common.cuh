@@ -100,9 +100,10 @@ struct MfMeta {
 int mf_prepass(const MfShape &sh, const float *d_templates, const int *d_moveouts,
                const float *d_weights, const float *d_data, MfMeta meta, float *d_energy,
                float *d_mean, cudaStream_t st);
-// sliding window energy (or its rsqrt) per channel, row pitch `out_pitch` elements
+// sliding window energy (or its rsqrt) per channel, row pitch `out_pitch` elements; phase8 writes
+// out[ch][j % 8][j / 8] (rows of out_pitch) instead of out[ch][j]
 int mf_energy(const MfShape &sh, const float *d_data, float *d_energy, float *d_mean, size_t out_pitch,
-              bool rsqrt_mode, cudaStream_t st);
+              bool rsqrt_mode, bool phase8, cudaStream_t st);
 int mf_fp32_run(const MfShape &sh, const float *d_templates, const int *d_moveouts,
                 const float *d_weights, const float *d_data, MfMeta meta, const float *d_energy,
                 const float *d_mean, float *d_cc, size_t cc_pitch, cudaStream_t st);

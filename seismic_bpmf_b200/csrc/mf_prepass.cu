@@ -89,10 +89,11 @@ __device__ __forceinline__ double block_exclusive_scan(double v, double *warp_to
 }
 
 // RSQRT: write 1/sqrt(E) (0 where E <= 0) instead of E -- the per-column factor of the tensor path.
+// phase8: write phase-major, out[ch][j % 8][j / 8] with rows of out_pitch elements (tensor path).
 template <bool FULL, bool RSQRT>
 __global__ void __launch_bounds__(EN_THREADS)
     mf_energy_kernel(const float *__restrict__ data, size_t N, size_t L, size_t n_win, size_t out_pitch,
-                     float *__restrict__ energy, float *__restrict__ mean) {
+                     int phase8, float *__restrict__ energy, float *__restrict__ mean) {
     extern __shared__ double sm[];
     __shared__ double warp_tot[EN_THREADS / 32];
     const size_t ch = blockIdx.y;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(EN_THREADS)
         if (FULL) P1[span] = tot1;
     }
     __syncthreads();
-    float *e = energy + ch * out_pitch + j0;
+    float *e = energy + (phase8 ? ch * 8 * out_pitch : ch * out_pitch + j0);
     float *m = FULL ? mean + ch * out_pitch + j0 : nullptr;
     for (size_t j = threadIdx.x; j < nj; j += EN_THREADS) {
         double ss = P2[j + L] - P2[j];
@@ -137,13 +138,15 @@ __global__ void __launch_bounds__(EN_THREADS)
             ss -= (double)L * mu * mu;
             m[j] = (float)mu;
         }
-        if (RSQRT) e[j] = (ss > 0.0) ? (float)(1.0 / sqrt(ss)) : 0.f;
-        else e[j] = (float)(ss > 0.0 ? ss : 0.0);
+        const size_t jg = j0 + j;
+        const size_t o = phase8 ? (jg & 7) * out_pitch + (jg >> 3) : j;
+        if (RSQRT) e[o] = (ss > 0.0) ? (float)(1.0 / sqrt(ss)) : 0.f;
+        else e[o] = (float)(ss > 0.0 ? ss : 0.0);
     }
 }
 
 int mf_energy(const MfShape &sh, const float *d_data, float *d_energy, float *d_mean, size_t out_pitch,
-              bool rsqrt_mode, cudaStream_t st) {
+              bool rsqrt_mode, bool phase8, cudaStream_t st) {
     const size_t n_win = sh.N - sh.L + 1;
     const bool full = sh.normalize != 0;
     const size_t span_max = (size_t)EN_BJ + sh.L;
@@ -155,7 +158,8 @@ int mf_energy(const MfShape &sh, const float *d_data, float *d_energy, float *d_
         BPMF_CUDA(cudaFuncSetAttribute(mf_energy_kernel<FU, RS>,                                   \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         mf_energy_kernel<FU, RS><<<grid, EN_THREADS, smem, st>>>(d_data, sh.N, sh.L, n_win,        \
-                                                                 out_pitch, d_energy, d_mean);     \
+                                                                 out_pitch, phase8 ? 1 : 0,        \
+                                                                 d_energy, d_mean);                \
     } while (0)
     if (full && rsqrt_mode) EN_LAUNCH(true, true);
     else if (full) EN_LAUNCH(true, false);
@@ -184,7 +188,7 @@ int mf_prepass(const MfShape &sh, const float *d_templates, const int *d_moveout
     }
     if (d_energy) {
         const size_t n_win = sh.N - sh.L + 1;
-        int rc = mf_energy(sh, d_data, d_energy, d_mean, n_win, false, st);
+        int rc = mf_energy(sh, d_data, d_energy, d_mean, n_win, false, false, st);
         if (rc != BPMF_OK) return rc;
     }
     return BPMF_OK;

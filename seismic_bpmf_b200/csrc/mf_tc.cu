@@ -21,8 +21,8 @@
 //     ring.  Templates longer than one resident image are cut into K chunks (numerators add).
 //   * BPMF_MF_TC_FP16X3: both operands are split hi + lo (two fp16 = 22 mantissa bits) and three
 //     MMAs (hi*hi + hi*lo + lo*hi) accumulate into the same TMEM tile: fp32-grade numerators.
-//   * epilogue (8 warps): tcgen05.ld -> * rsqrt(window energy)[column] * weight/|T|[row] ->
-//     red.global.add.f32 into cc_sum.  Work is ordered segment -> template tile -> channel so the
+//   * epilogue (8 warps): tcgen05.ld -> * rsqrt(window energy)[column] (phase-major global copy,
+//     prefetched one chunk ahead with LDG.128) * weight/|T|[row] -> red.global.add.f32 into cc_sum.  Work is ordered segment -> template tile -> channel so the
 //     48 channel-CTAs that add into the same 16 rows x 131 072 samples do so while that region
 //     (8 MB) is L2 resident.
 //
@@ -41,7 +41,7 @@ constexpr int TC_KC_MAX = 816;      // resident A, single pass: 128 x 816 fp16 =
 constexpr int TC_KC_MAX_SPLIT = 384; // resident A, hi + lo images: 128 x 384 x 2 x 2 = 196 608 B
 constexpr int TC_SEG_TILES = 64;    // tiles swept per resident A image
 constexpr int TC_THREADS = 320;     // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
-constexpr int TC_INV_SLOT = 1056;   // floats per half-tile slot (needs 1024 + 8)
+constexpr int TC_NB = 3;            // trace-slice (B operand) stages
 constexpr int TC_TMEM_COLS = 512;
 
 constexpr size_t TC_SMEM_LIMIT = 232448;  // 227 KB opt-in shared memory per CTA
@@ -50,8 +50,8 @@ struct TcParams {
     const __half *dh;        // (SC, dh_pitch) scaled fp16 traces (hi part), zero padded
     const __half *dh_lo;     // residual x*s - hi (split mode only)
     size_t dh_pitch;
-    const float *colinv;     // (SC, ci_pitch) rsqrt(window energy), 0 where undefined
-    size_t ci_pitch;
+    const float *colinv;     // (SC, 8, ci_pitch) phase-major rsqrt(window energy): [ch][j % 8][j / 8],
+    size_t ci_pitch;         // 0 where undefined
     const uint8_t *aimg;     // (SC, MT, n_kc) A images in UMMA core-matrix order, a_bytes each
                              // (split mode: hi image followed by lo image)
     const int *row_q;        // (SC, MT, 128) whole-column shift of the row
@@ -69,6 +69,17 @@ struct TcParams {
 struct TcItem {
     int kc, ch, mt, seg;
 };
+// Tiles of a segment are visited in a rotated order that depends on the channel: the CTAs that add
+// into the same cc_sum rows (one per channel) then work on different columns at any instant, so
+// their reductions do not queue on the same L2 sectors.
+__device__ __forceinline__ int tc_tile(int t_begin, int n_t, int rot, int k) {
+    int x = k + rot;
+    if (x >= n_t) x -= n_t;
+    return t_begin + x;
+}
+__device__ __forceinline__ int tc_rot(const TcParams &p, int ch, int kc, int n_t) {
+    return (int)(((unsigned)(ch * p.n_kc + kc) * 2654435761u >> 8) % (unsigned)n_t);
+}
 __device__ __forceinline__ TcItem tc_decode(const TcParams &p, int it) {
     TcItem r;
     r.kc = it % p.n_kc;
@@ -168,18 +179,54 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive columns of this lane's phase row of rsqrt(energy): 8 x LDG.128 (jj multiple of 32)
+__device__ __forceinline__ void tc_inv_load(float4 (&iv)[8], const float4 *base, long long jj) {
+    const float4 *src = base + (jj >> 2);
+#pragma unroll
+    for (int i = 0; i < 8; i++) iv[i] = __ldg(src + i);
+}
+__device__ __forceinline__ float f4_get(const float4 &v, int i) {
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+// one 32-column chunk of the epilogue: TMEM -> registers -> normalise -> red.global.add
+// mode 2: every lane's 128 columns are valid; 1: per-column predicate; 0: nothing to write
+__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float4 (&iv)[8], float *dst, int c0, int c_lo,
+                                             int c_hi, int mode, float ithr, float scale,
+                                             uint64_t *release = nullptr, int lane = 0) {
+    float v[32];
+    tc_ld32(taddr, v);
+    if (release != nullptr) {  // accumulator stage fully read by this warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release);
+    }
+    if (mode == 2) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const float w = f4_get(iv[c >> 2], c & 3);
+            const float x = v[c] * w;
+            atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
+        }
+    } else if (mode == 1) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const float w = f4_get(iv[c >> 2], c & 3);
+            const float x = v[c] * w;
+            if (c0 + c >= c_lo && c0 + c < c_hi) atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a_s = smem;
     uint8_t *b_s = smem + p.a_bytes;
-    float *inv_s = reinterpret_cast<float *>(b_s + 2 * p.b_stage_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(inv_s + 2 * TC_INV_SLOT);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_s + TC_NB * p.b_stage_bytes);
     uint64_t *a_full = bars + 0, *a_empty = bars + 1;
-    uint64_t *b_full = bars + 2, *b_empty = bars + 4;          // [2]
-    uint64_t *acc_full = bars + 6, *acc_empty = bars + 8;      // [2]
-    uint64_t *inv_full = bars + 10, *inv_empty = bars + 12;    // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+    uint64_t *acc_full = bars + 2, *acc_empty = bars + 4;               // [2]
+    uint64_t *b_full = bars + 6, *b_empty = bars + 6 + TC_NB;           // [TC_NB]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 + 2 * TC_NB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -187,12 +234,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < 2; i++) {
-            mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 1);
             mbar_init(acc_full + i, 1);
             mbar_init(acc_empty + i, 8);  // one arrive per epilogue warp
-            mbar_init(inv_full + i, 1);
-            mbar_init(inv_empty + i, 4);  // the four warps that read this half
+        }
+        for (int i = 0; i < TC_NB; i++) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -209,10 +256,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
 
     const int n_items = p.n_seg * p.MT * p.SC * p.n_kc;
     const uint32_t b_bytes = (uint32_t)p.b_slice_bytes;  // (8*255 + Kc) * 2, a multiple of 16
-    const uint32_t inv_bytes = (1024 + 8) * 4;
 
     if (warp == 0) {
-        // ===================== producer: bulk copies of A images, trace slices, rsqrt(energy) =====
+        // ===================== producer: bulk copies of A images and trace slices ==================
         if (lane == 0) {
             uint32_t n_item = 0, n_tile = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -229,21 +275,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 n_item++;
                 const int t_begin = seg * p.seg_tiles;
                 const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
-                for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
-                    const int s = n_tile & 1;
-                    const uint32_t par = ((n_tile >> 1) & 1) ^ 1;
+                const int n_t = t_end - t_begin, rot = tc_rot(p, ch, im.kc, n_t);
+                for (int k = 0; k < n_t; k++, n_tile++) {
+                    const int tile = tc_tile(t_begin, n_t, rot, k);
+                    const int s = n_tile % TC_NB;
+                    const uint32_t par = ((n_tile / TC_NB) & 1) ^ 1;
                     mbar_wait(b_empty + s, par);
                     const size_t d_off = (size_t)ch * p.dh_pitch + (size_t)tile * (8 * TC_NCOL) + (size_t)im.kc * p.Kc;
                     mbar_expect_tx(b_full + s, p.split ? 2 * b_bytes : b_bytes);
                     bulk_g2s(b_s + s * p.b_stage_bytes, p.dh + d_off, b_bytes, b_full + s);
                     if (p.split) bulk_g2s(b_s + s * p.b_stage_bytes + b_bytes, p.dh_lo + d_off, b_bytes, b_full + s);
-                    const float *ci = p.colinv + (size_t)ch * p.ci_pitch + (size_t)tile * (8 * TC_NCOL);
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        mbar_wait(inv_empty + h, (n_tile & 1) ^ 1);
-                        mbar_expect_tx(inv_full + h, inv_bytes);
-                        bulk_g2s(inv_s + h * TC_INV_SLOT, ci + h * 1024, inv_bytes, inv_full + h);
-                    }
                 }
             }
         }
@@ -262,13 +303,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 n_item++;
                 const int t_begin = seg * p.seg_tiles;
                 const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
-                for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
-                    const int s = n_tile & 1;
-                    const uint32_t par = (n_tile >> 1) & 1;
-                    mbar_wait(b_full + s, par);
-                    mbar_wait(acc_empty + s, par ^ 1);
+                for (int k = t_begin; k < t_end; k++, n_tile++) {
+                    const int s = n_tile % TC_NB;      // trace-slice stage
+                    const int sa = n_tile & 1;         // accumulator stage
+                    mbar_wait(b_full + s, (n_tile / TC_NB) & 1);
+                    mbar_wait(acc_empty + sa, ((n_tile >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_NCOL);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(sa * TC_NCOL);
                     for (int kk = 0; kk < n_k; kk++) {
                         // A: K chunk c of 8 elements lives at c * (128 rows * 16 B); rows 16 B apart
                         const uint64_t da = tc_desc(a_addr + (uint32_t)kk * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
@@ -284,8 +325,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                             tc_mma_f16(d_tmem, da_lo, db, idesc, 1u);
                         }
                     }
-                    tc_commit(b_empty + s);   // trace slice may be overwritten once these MMAs retire
-                    tc_commit(acc_full + s);  // accumulator ready for the epilogue
+                    tc_commit(b_empty + s);    // trace slice may be overwritten once these MMAs retire
+                    tc_commit(acc_full + sa);  // accumulator ready for the epilogue
                 }
                 tc_commit(a_empty);  // A image may be replaced once every MMA of this item retired
             }
@@ -320,48 +361,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
             float *out_row = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + ir;
             const int t_begin = seg * p.seg_tiles;
             const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
-            for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
+            // rsqrt(window energy) of this row's columns: phase-major copy, contiguous in jj, prefetched
+            // one 32-column chunk ahead straight into registers (no shared-memory staging)
+            const float4 *inv4 = reinterpret_cast<const float4 *>(p.colinv + ((size_t)ch * 8 + e) * p.ci_pitch);
+            float4 iv_a[8], iv_b[8];
+            const int n_t = t_end - t_begin, rot = tc_rot(p, ch, im.kc, n_t);
+            tc_inv_load(iv_a, inv4, (long long)tc_tile(t_begin, n_t, rot, 0) * TC_NCOL + half * 128);
+            for (int k = 0; k < n_t; k++, n_tile++) {
+                const int tile = tc_tile(t_begin, n_t, rot, k);
                 const int s = n_tile & 1;
                 mbar_wait(acc_full + s, (n_tile >> 1) & 1);
-                mbar_wait(inv_full + half, n_tile & 1);
                 tc_fence_after();
-                const float *inv = inv_s + half * TC_INV_SLOT + e;
                 const long long jj0 = (long long)tile * TC_NCOL + half * 128;  // first column of this half
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_NCOL + half * 128);
                 // columns of this half that are valid for this row: [c_lo, c_hi)
                 long long c_lo64 = jj_lo - jj0, c_hi64 = jj_hi - jj0 + 1;
                 const int c_lo = (int)(c_lo64 < 0 ? 0 : (c_lo64 > 128 ? 128 : c_lo64));
                 const int c_hi = (int)(c_hi64 > 128 ? 128 : (c_hi64 < 0 ? 0 : c_hi64));
-                const bool any_valid = __any_sync(0xffffffffu, c_hi > c_lo);
-                const bool all_valid = __all_sync(0xffffffffu, c_lo == 0 && c_hi == 128);
-#pragma unroll 1
-                for (int chunk = 0; chunk < 4; chunk++) {
-                    float v[32];
-                    tc_ld32(taddr + (uint32_t)(chunk * 32), v);
-                    float *dst = out_row + 8 * (jj0 + chunk * 32 - q);
-                    const float *ivc = inv + 8 * (chunk * 32);
-                    if (all_valid) {
+                const int mode = __all_sync(0xffffffffu, c_lo == 0 && c_hi == 128)
+                                     ? 2 : (__any_sync(0xffffffffu, c_hi > c_lo) ? 1 : 0);
+                const long long jj_next =  // next tile visited, same half (prefetch only)
+                    (k + 1 < n_t) ? (long long)tc_tile(t_begin, n_t, rot, k + 1) * TC_NCOL + half * 128 : jj0;
+                float *dst = out_row + 8 * (jj0 - q);
 #pragma unroll
-                        for (int c = 0; c < 32; c++) {
-                            const float w = ivc[8 * c];
-                            const float x = v[c] * w;
-                            atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
-                        }
-                    } else if (any_valid) {
-#pragma unroll
-                        for (int c = 0; c < 32; c++) {
-                            const int col = chunk * 32 + c;
-                            const float w = ivc[8 * c];
-                            const float x = v[c] * w;
-                            if (col >= c_lo && col < c_hi) atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
-                        }
+                for (int pair = 0; pair < 2; pair++) {
+                    const int c0 = pair * 64;
+                    tc_inv_load(iv_b, inv4, jj0 + c0 + 32);
+                    tc_epi_chunk(taddr + (uint32_t)c0, iv_a, dst + 8 * c0, c0, c_lo, c_hi, mode, ithr, scale);
+                    tc_inv_load(iv_a, inv4, pair == 0 ? jj0 + 64 : jj_next);
+                    if (pair == 1) {
+                        // last TMEM read of this accumulator stage is issued inside the next call; the
+                        // stage is released right after it completes, before the reductions drain
+                        tc_epi_chunk(taddr + (uint32_t)(c0 + 32), iv_b, dst + 8 * (c0 + 32), c0 + 32, c_lo, c_hi, mode,
+                                     ithr, scale, acc_empty + s, lane);
+                    } else {
+                        tc_epi_chunk(taddr + (uint32_t)(c0 + 32), iv_b, dst + 8 * (c0 + 32), c0 + 32, c_lo, c_hi, mode,
+                                     ithr, scale);
                     }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(acc_empty + s);
-                    mbar_arrive(inv_empty + half);
                 }
             }
         }
@@ -505,18 +541,18 @@ static TcWs tc_carve(Workspace &ws, const MfShape &sh, int split) {
     w.a_bytes = w.a_img_bytes * (split ? 2 : 1);
     w.b_slice_bytes = (8 * (TC_NCOL - 1) + w.Kc) * 2;
     w.b_stage_bytes = (int)align_up((size_t)w.b_slice_bytes * (split ? 2 : 1), 128);
-    w.smem_bytes = (size_t)w.a_bytes + 2 * (size_t)w.b_stage_bytes + 2 * TC_INV_SLOT * 4 + 256;
+    w.smem_bytes = (size_t)w.a_bytes + TC_NB * (size_t)w.b_stage_bytes + 256;
     w.MT = (int)((sh.T + TC_TPL - 1) / TC_TPL);
     const size_t n_cols = (sh.N - sh.L) / 8 + 1;  // GEMM columns that can hold a valid window start
     w.n_tiles = (int)((n_cols + TC_NCOL - 1) / TC_NCOL);
     // last slice read: (n_tiles-1)*2048 + (n_kc-1)*Kc + 2040 + Kc
     w.dh_pitch = align_up((size_t)w.n_tiles * (8 * TC_NCOL) + (size_t)w.n_kc * w.Kc + 64, 64);
     if (w.dh_pitch < align_up(sh.N, 64)) w.dh_pitch = align_up(sh.N, 64);
-    w.ci_pitch = (size_t)w.n_tiles * (8 * TC_NCOL) + 64;
+    w.ci_pitch = (size_t)w.n_tiles * TC_NCOL + 64;  // columns per phase row
     const size_t SC = sh.SC();
     w.dh = ws.take<__half>(SC * w.dh_pitch);
     w.dh_lo = split ? ws.take<__half>(SC * w.dh_pitch) : nullptr;
-    w.colinv = ws.take<float>(SC * w.ci_pitch);
+    w.colinv = ws.take<float>(SC * 8 * w.ci_pitch);
     w.aimg = ws.take<uint8_t>(SC * (size_t)w.MT * w.n_kc * w.a_bytes);
     w.row_q = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
     w.row_e = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
@@ -556,8 +592,8 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     tc_data_convert_kernel<<<dim3(128, (unsigned)SC), 256, 0, st>>>(d_data, sh.N, w.dh_pitch, w.chmax, w.dh,
                                                                     w.dh_lo, w.ch_scale);
     BPMF_LAUNCH_CHECK();
-    BPMF_CUDA(cudaMemsetAsync(w.colinv, 0, sizeof(float) * SC * w.ci_pitch, st));
-    int rc = mf_energy(sh, d_data, w.colinv, nullptr, w.ci_pitch, true, st);
+    BPMF_CUDA(cudaMemsetAsync(w.colinv, 0, sizeof(float) * SC * 8 * w.ci_pitch, st));
+    int rc = mf_energy(sh, d_data, w.colinv, nullptr, w.ci_pitch, true, true, st);
     if (rc != BPMF_OK) return rc;
     // templates: resident A images + per-row constants
     tc_template_prep_kernel<<<dim3((unsigned)w.MT, (unsigned)SC), TC_ROWS, 0, st>>>(
