@@ -13,22 +13,23 @@
 //     no-swizzle K-major core matrix: the UMMA descriptor (LBO = 16 B, SBO = 128 B) walks a Hankel
 //     view of the trace without any im2col copy.  One 5.7 KB slice of trace feeds a 128 x 256 tile.
 //   * the 8 sub-row alignments ("phases") of a template are 8 ROWS of A: row (t, r) holds template
-//     t delayed by e = (r + moveout) mod 8 samples, so that row produces outputs i = r (mod 8) and
-//     its 8 lanes x 1 column form one aligned 32-byte sector of cc_sum.  The whole-column part of
-//     the moveout, q = floor((r + moveout) / 8), is applied as an output address shift.
+//     t delayed by e = r + (moveout mod 8) samples, so that row produces outputs i = r (mod 8) and
+//     the 8 lanes x 1 column of a template form ONE aligned 32-byte sector of cc_sum.  The
+//     whole-column part of the moveout, q = floor(moveout / 8), is an output address shift.
 //   * A (16 templates x 8 phases x Kc, up to 204 KB) stays RESIDENT in shared memory while the CTA
 //     sweeps a segment of 64 tiles (131 072 samples); B slices stream through a 2-stage bulk-copy
 //     ring.  Templates longer than one resident image are cut into K chunks (numerators add).
 //   * BPMF_MF_TC_FP16X3: both operands are split hi + lo (two fp16 = 22 mantissa bits) and three
 //     MMAs (hi*hi + hi*lo + lo*hi) accumulate into the same TMEM tile: fp32-grade numerators.
-//   * epilogue (8 warps): tcgen05.ld -> * rsqrt(window energy)[column] (phase-major global copy,
-//     prefetched one chunk ahead with LDG.128) * weight/|T|[row] -> red.global.add.f32 into cc_sum.  Work is ordered segment -> template tile -> channel so the
+//   * epilogue (8 warps): tcgen05.ld -> * rsqrt(window energy)[column] (32-column slices staged in
+//     shared memory by a dedicated bulk-copy warp) * weight/|T|[row] -> red.global.add.f32 into cc_sum.  Work is ordered segment -> template tile -> channel so the
 //     48 channel-CTAs that add into the same 16 rows x 131 072 samples do so while that region
 //     (8 MB) is L2 resident.
 //
 // Rooflines: tensor pipe (2*Kp flop per output, Kp = L+7 rounded to 16) and L2 reduction
 // throughput (one fp32 red per (template, channel, output); ~850 Gred/s measured, tools/red_bench.cu).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -40,9 +41,14 @@ constexpr int TC_NCOL = 256;        // GEMM columns per tile (= 2048 samples)
 constexpr int TC_KC_MAX = 816;      // resident A, single pass: 128 x 816 fp16 = 208 896 B
 constexpr int TC_KC_MAX_SPLIT = 384; // resident A, hi + lo images: 128 x 384 x 2 x 2 = 196 608 B
 constexpr int TC_SEG_TILES = 64;    // tiles swept per resident A image
-constexpr int TC_THREADS = 320;     // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
-constexpr int TC_NB = 3;            // trace-slice (B operand) stages
+constexpr int TC_THREADS = 352;     // warp 0 A/B producer, warp 1 MMA, warps 2-9 epilogue, warp 10 rsqrt producer
+constexpr int TC_EPI_WARP0 = 2;
+constexpr int TC_NB = 2;            // trace-slice (B operand) stages
+constexpr int TC_NI = 5;            // rsqrt(energy) slots per tile half (32 columns each)
+constexpr int TC_INV_SLOT = 264;    // floats per slot: 8 * 32 columns + 8 (row delays reach 14)
 constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_FRONT = 8;         // zero samples in front of every staged trace: column jj starts at
+                                    // sample 8*(jj-1), so rows delayed by e >= 8 still reach samples 0..7
 
 constexpr size_t TC_SMEM_LIMIT = 232448;  // 227 KB opt-in shared memory per CTA
 
@@ -50,12 +56,12 @@ struct TcParams {
     const __half *dh;        // (SC, dh_pitch) scaled fp16 traces (hi part), zero padded
     const __half *dh_lo;     // residual x*s - hi (split mode only)
     size_t dh_pitch;
-    const float *colinv;     // (SC, 8, ci_pitch) phase-major rsqrt(window energy): [ch][j % 8][j / 8],
-    size_t ci_pitch;         // 0 where undefined
+    const float *colinv;     // (SC, ci_pitch) rsqrt(window energy) per window start, 0 where undefined
+    size_t ci_pitch;
     const uint8_t *aimg;     // (SC, MT, n_kc) A images in UMMA core-matrix order, a_bytes each
                              // (split mode: hi image followed by lo image)
-    const int *row_q;        // (SC, MT, 128) whole-column shift of the row
-    const int *row_e;        // (SC, MT, 128) sub-column delay folded into the A row
+    const int *row_q;        // (SC, MT, 128) whole-column shift floor(moveout / 8), same for a template's 8 rows
+    const int *row_e;        // (SC, MT, 128) delay folded into the A row: phase + moveout mod 8, in [0, 15)
     const float *row_scale;  // (SC, MT, 128) weight / (sA * sB * sqrt(sum T^2)), 0 = unused row
     const float *row_ithr;   // (SC, MT, 128) guard: contribute only where colinv < ithr
     const int *item_active;  // (SC, MT)
@@ -64,22 +70,12 @@ struct TcParams {
     size_t cc_pitch;
     int T, SC, MT, n_kc, Kc, split, a_bytes, a_img_bytes, b_slice_bytes, b_stage_bytes;
     int n_tiles, seg_tiles, n_seg;
+    int debug;  // BPMF_TC_DEBUG bit 0: skip the reductions (perf triage only)
 };
 
 struct TcItem {
     int kc, ch, mt, seg;
 };
-// Tiles of a segment are visited in a rotated order that depends on the channel: the CTAs that add
-// into the same cc_sum rows (one per channel) then work on different columns at any instant, so
-// their reductions do not queue on the same L2 sectors.
-__device__ __forceinline__ int tc_tile(int t_begin, int n_t, int rot, int k) {
-    int x = k + rot;
-    if (x >= n_t) x -= n_t;
-    return t_begin + x;
-}
-__device__ __forceinline__ int tc_rot(const TcParams &p, int ch, int kc, int n_t) {
-    return (int)(((unsigned)(ch * p.n_kc + kc) * 2654435761u >> 8) % (unsigned)n_t);
-}
 __device__ __forceinline__ TcItem tc_decode(const TcParams &p, int it) {
     TcItem r;
     r.kc = it % p.n_kc;
@@ -179,38 +175,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// 32 consecutive columns of this lane's phase row of rsqrt(energy): 8 x LDG.128 (jj multiple of 32)
-__device__ __forceinline__ void tc_inv_load(float4 (&iv)[8], const float4 *base, long long jj) {
-    const float4 *src = base + (jj >> 2);
-#pragma unroll
-    for (int i = 0; i < 8; i++) iv[i] = __ldg(src + i);
-}
-__device__ __forceinline__ float f4_get(const float4 &v, int i) {
-    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
-}
 // one 32-column chunk of the epilogue: TMEM -> registers -> normalise -> red.global.add
-// mode 2: every lane's 128 columns are valid; 1: per-column predicate; 0: nothing to write
-__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float4 (&iv)[8], float *dst, int c0, int c_lo,
-                                             int c_hi, int mode, float ithr, float scale,
-                                             uint64_t *release = nullptr, int lane = 0) {
+// mode 2: every lane's 128 columns are valid; 1: per-column predicate; 0: nothing to write.
+// inv points at this row's first rsqrt(energy) value of the chunk; column c lives 8*c floats on.
+__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, float *dst, int c0, int c_lo,
+                                             int c_hi, int mode, float ithr, float scale, int debug) {
     float v[32];
     tc_ld32(taddr, v);
-    if (release != nullptr) {  // accumulator stage fully read by this warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(release);
-    }
+    if (debug & 1) mode = (v[0] == 12345.678f) ? mode : 0;  // triage: keep everything but the reductions
     if (mode == 2) {
 #pragma unroll
         for (int c = 0; c < 32; c++) {
-            const float w = f4_get(iv[c >> 2], c & 3);
+            const float w = inv[8 * c];
             const float x = v[c] * w;
             atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
         }
     } else if (mode == 1) {
 #pragma unroll
         for (int c = 0; c < 32; c++) {
-            const float w = f4_get(iv[c >> 2], c & 3);
+            const float w = inv[8 * c];
             const float x = v[c] * w;
             if (c0 + c >= c_lo && c0 + c < c_hi) atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
         }
@@ -222,11 +205,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a_s = smem;
     uint8_t *b_s = smem + p.a_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(b_s + TC_NB * p.b_stage_bytes);
+    float *inv_s = reinterpret_cast<float *>(b_s + TC_NB * p.b_stage_bytes);  // [2 halves][TC_NI][TC_INV_SLOT]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(inv_s + 2 * TC_NI * TC_INV_SLOT);
     uint64_t *a_full = bars + 0, *a_empty = bars + 1;
     uint64_t *acc_full = bars + 2, *acc_empty = bars + 4;               // [2]
     uint64_t *b_full = bars + 6, *b_empty = bars + 6 + TC_NB;           // [TC_NB]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 + 2 * TC_NB);
+    uint64_t *inv_full = bars + 6 + 2 * TC_NB;                          // [2][TC_NI]
+    uint64_t *inv_empty = inv_full + 2 * TC_NI;                         // [2][TC_NI]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(inv_empty + 2 * TC_NI);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -240,6 +226,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
         for (int i = 0; i < TC_NB; i++) {
             mbar_init(b_full + i, 1);
             mbar_init(b_empty + i, 1);
+        }
+        for (int i = 0; i < 2 * TC_NI; i++) {
+            mbar_init(inv_full + i, 1);
+            mbar_init(inv_empty + i, 4);  // the four warps that read this half
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -275,12 +265,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 n_item++;
                 const int t_begin = seg * p.seg_tiles;
                 const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
-                const int n_t = t_end - t_begin, rot = tc_rot(p, ch, im.kc, n_t);
-                for (int k = 0; k < n_t; k++, n_tile++) {
-                    const int tile = tc_tile(t_begin, n_t, rot, k);
+                for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
                     const int s = n_tile % TC_NB;
-                    const uint32_t par = ((n_tile / TC_NB) & 1) ^ 1;
-                    mbar_wait(b_empty + s, par);
+                    mbar_wait(b_empty + s, ((n_tile / TC_NB) & 1) ^ 1);
                     const size_t d_off = (size_t)ch * p.dh_pitch + (size_t)tile * (8 * TC_NCOL) + (size_t)im.kc * p.Kc;
                     mbar_expect_tx(b_full + s, p.split ? 2 * b_bytes : b_bytes);
                     bulk_g2s(b_s + s * p.b_stage_bytes, p.dh + d_off, b_bytes, b_full + s);
@@ -331,12 +318,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 tc_commit(a_empty);  // A image may be replaced once every MMA of this item retired
             }
         }
+    } else if (warp == TC_EPI_WARP0 + 8) {
+        // ===================== rsqrt(energy) producer: 32-column slices for the epilogue ===========
+        if (lane == 0) {
+            uint32_t n_chunk = 0;  // per half: chunks issued so far
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const TcItem im = tc_decode(p, it);
+                const int ch = im.ch, mt = im.mt, seg = im.seg;
+                if (!p.item_active[ch * p.MT + mt]) continue;
+                const int t_begin = seg * p.seg_tiles;
+                const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+                const float *ci = p.colinv + (size_t)ch * p.ci_pitch;
+                for (int tile = t_begin; tile < t_end; tile++) {
+                    for (int chunk = 0; chunk < 4; chunk++, n_chunk++) {
+                        const int slot = n_chunk % TC_NI;
+                        const uint32_t par = ((n_chunk / TC_NI) & 1) ^ 1;
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            uint64_t *full = inv_full + h * TC_NI + slot;
+                            mbar_wait(inv_empty + h * TC_NI + slot, par);
+                            mbar_expect_tx(full, TC_INV_SLOT * 4);
+                            bulk_g2s(inv_s + (h * TC_NI + slot) * TC_INV_SLOT,
+                                     ci + 8 * ((size_t)tile * TC_NCOL + h * 128 + chunk * 32), TC_INV_SLOT * 4, full);
+                        }
+                    }
+                }
+            }
+        }
     } else {
         // ===================== epilogue: TMEM -> normalise -> red.add into cc_sum ==================
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;        // which 128 columns of the tile
-        const int row = quarter * 32 + lane;     // A row == TMEM lane
-        uint32_t n_tile = 0;
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+        const int half = (warp - TC_EPI_WARP0) >> 2;       // which 128 columns of the tile
+        const int row = quarter * 32 + lane;               // A row == TMEM lane
+        uint32_t n_tile = 0, n_chunk = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const TcItem im = tc_decode(p, it);
             const int ch = im.ch, mt = im.mt, seg = im.seg;
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
             const float scale = p.row_scale[mrow];
             const float ithr = p.row_ithr[mrow];
             const int q = p.row_q[mrow];
-            const int e = p.row_e[mrow];
+            const int e = p.row_e[mrow];  // in [0, 15)
             const int t = mt * TC_TPL + (row >> 3);
             const int ir = row & 7;
             int lo = 1, hi = 0;
@@ -361,14 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
             float *out_row = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + ir;
             const int t_begin = seg * p.seg_tiles;
             const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
-            // rsqrt(window energy) of this row's columns: phase-major copy, contiguous in jj, prefetched
-            // one 32-column chunk ahead straight into registers (no shared-memory staging)
-            const float4 *inv4 = reinterpret_cast<const float4 *>(p.colinv + ((size_t)ch * 8 + e) * p.ci_pitch);
-            float4 iv_a[8], iv_b[8];
-            const int n_t = t_end - t_begin, rot = tc_rot(p, ch, im.kc, n_t);
-            tc_inv_load(iv_a, inv4, (long long)tc_tile(t_begin, n_t, rot, 0) * TC_NCOL + half * 128);
-            for (int k = 0; k < n_t; k++, n_tile++) {
-                const int tile = tc_tile(t_begin, n_t, rot, k);
+            for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
                 const int s = n_tile & 1;
                 mbar_wait(acc_full + s, (n_tile >> 1) & 1);
                 tc_fence_after();
@@ -380,25 +387,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 const int c_hi = (int)(c_hi64 > 128 ? 128 : (c_hi64 < 0 ? 0 : c_hi64));
                 const int mode = __all_sync(0xffffffffu, c_lo == 0 && c_hi == 128)
                                      ? 2 : (__any_sync(0xffffffffu, c_hi > c_lo) ? 1 : 0);
-                const long long jj_next =  // next tile visited, same half (prefetch only)
-                    (k + 1 < n_t) ? (long long)tc_tile(t_begin, n_t, rot, k + 1) * TC_NCOL + half * 128 : jj0;
                 float *dst = out_row + 8 * (jj0 - q);
-#pragma unroll
-                for (int pair = 0; pair < 2; pair++) {
-                    const int c0 = pair * 64;
-                    tc_inv_load(iv_b, inv4, jj0 + c0 + 32);
-                    tc_epi_chunk(taddr + (uint32_t)c0, iv_a, dst + 8 * c0, c0, c_lo, c_hi, mode, ithr, scale);
-                    tc_inv_load(iv_a, inv4, pair == 0 ? jj0 + 64 : jj_next);
-                    if (pair == 1) {
-                        // last TMEM read of this accumulator stage is issued inside the next call; the
-                        // stage is released right after it completes, before the reductions drain
-                        tc_epi_chunk(taddr + (uint32_t)(c0 + 32), iv_b, dst + 8 * (c0 + 32), c0 + 32, c_lo, c_hi, mode,
-                                     ithr, scale, acc_empty + s, lane);
-                    } else {
-                        tc_epi_chunk(taddr + (uint32_t)(c0 + 32), iv_b, dst + 8 * (c0 + 32), c0 + 32, c_lo, c_hi, mode,
-                                     ithr, scale);
-                    }
+#pragma unroll 1
+                for (int chunk = 0; chunk < 4; chunk++, n_chunk++) {
+                    const int slot = n_chunk % TC_NI;
+                    uint64_t *full = inv_full + half * TC_NI + slot;
+                    mbar_wait(full, (n_chunk / TC_NI) & 1);
+                    const float *inv = inv_s + (half * TC_NI + slot) * TC_INV_SLOT + e;
+                    tc_epi_chunk(taddr + (uint32_t)(chunk * 32), inv, dst + 8 * (chunk * 32), chunk * 32, c_lo, c_hi,
+                                 mode, ithr, scale, p.debug);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(inv_empty + half * TC_NI + slot);
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + s);
             }
         }
     }
@@ -448,7 +451,7 @@ __global__ void tc_data_convert_kernel(const float *__restrict__ data, size_t N,
     __half *o = dh + ch * dh_pitch;
     __half *ol = dh_lo ? dh_lo + ch * dh_pitch : nullptr;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dh_pitch; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = i < N ? d[i] * sB : 0.f;
+        const float v = (i >= TC_FRONT && i - TC_FRONT < N) ? d[i - TC_FRONT] * sB : 0.f;
         const __half h = __float2half_rn(v);
         o[i] = h;
         if (ol) ol[i] = __float2half_rn(v - __half2float(h));
@@ -484,9 +487,12 @@ __global__ void __launch_bounds__(TC_ROWS)
     const int any = __syncthreads_or(used ? 1 : 0);
     if (row == 0) item_active[item] = any;
 
-    const int sum = ir + m;
-    const int q = (sum >= 0) ? (sum >> 3) : -((-sum + 7) >> 3);  // floor(sum / 8)
-    const int e = sum - 8 * q;                                   // in [0, 8)
+    // window start of output i = 8*ii + ir is j = i + m = 8*(ii + q) + ir + (m - 8q): the whole-column
+    // part q = floor(m / 8) is the same for the template's 8 rows (so the 8 lanes of a column add
+    // into ONE aligned 32-byte sector); the rest, e = ir + m mod 8 in [0, 15), is a delay of the row
+    const int q0 = (m >= 0) ? (m >> 3) : -((-m + 7) >> 3);
+    const int e = ir + (m - 8 * q0);
+    const int q = q0 + TC_FRONT / 8;  // staged traces start TC_FRONT samples early
     const float *tp = templates + ((size_t)(t < T ? t : 0) * SC + ch) * (size_t)L;
     float sA = 1.f;
     if (used) {
@@ -533,7 +539,7 @@ struct TcWs {
 
 static TcWs tc_carve(Workspace &ws, const MfShape &sh, int split) {
     TcWs w;
-    const int Kp = (int)align_up(sh.L + 7, 16);
+    const int Kp = (int)align_up(sh.L + 14, 16);  // template length + largest row delay
     const int kc_max = split ? TC_KC_MAX_SPLIT : TC_KC_MAX;
     w.n_kc = (Kp + kc_max - 1) / kc_max;
     w.Kc = (int)align_up((size_t)(Kp + w.n_kc - 1) / w.n_kc, 16);
@@ -541,18 +547,18 @@ static TcWs tc_carve(Workspace &ws, const MfShape &sh, int split) {
     w.a_bytes = w.a_img_bytes * (split ? 2 : 1);
     w.b_slice_bytes = (8 * (TC_NCOL - 1) + w.Kc) * 2;
     w.b_stage_bytes = (int)align_up((size_t)w.b_slice_bytes * (split ? 2 : 1), 128);
-    w.smem_bytes = (size_t)w.a_bytes + TC_NB * (size_t)w.b_stage_bytes + 256;
+    w.smem_bytes = (size_t)w.a_bytes + TC_NB * (size_t)w.b_stage_bytes + 2 * TC_NI * TC_INV_SLOT * 4 + 320;
     w.MT = (int)((sh.T + TC_TPL - 1) / TC_TPL);
-    const size_t n_cols = (sh.N - sh.L) / 8 + 1;  // GEMM columns that can hold a valid window start
+    const size_t n_cols = (sh.N - sh.L + TC_FRONT) / 8 + 1;  // GEMM columns that can hold a valid window start
     w.n_tiles = (int)((n_cols + TC_NCOL - 1) / TC_NCOL);
     // last slice read: (n_tiles-1)*2048 + (n_kc-1)*Kc + 2040 + Kc
     w.dh_pitch = align_up((size_t)w.n_tiles * (8 * TC_NCOL) + (size_t)w.n_kc * w.Kc + 64, 64);
-    if (w.dh_pitch < align_up(sh.N, 64)) w.dh_pitch = align_up(sh.N, 64);
-    w.ci_pitch = (size_t)w.n_tiles * TC_NCOL + 64;  // columns per phase row
+    if (w.dh_pitch < align_up(sh.N + TC_FRONT, 64)) w.dh_pitch = align_up(sh.N + TC_FRONT, 64);
+    w.ci_pitch = (size_t)w.n_tiles * (8 * TC_NCOL) + 64;
     const size_t SC = sh.SC();
     w.dh = ws.take<__half>(SC * w.dh_pitch);
     w.dh_lo = split ? ws.take<__half>(SC * w.dh_pitch) : nullptr;
-    w.colinv = ws.take<float>(SC * 8 * w.ci_pitch);
+    w.colinv = ws.take<float>(SC * w.ci_pitch);
     w.aimg = ws.take<uint8_t>(SC * (size_t)w.MT * w.n_kc * w.a_bytes);
     w.row_q = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
     w.row_e = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
@@ -592,8 +598,8 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     tc_data_convert_kernel<<<dim3(128, (unsigned)SC), 256, 0, st>>>(d_data, sh.N, w.dh_pitch, w.chmax, w.dh,
                                                                     w.dh_lo, w.ch_scale);
     BPMF_LAUNCH_CHECK();
-    BPMF_CUDA(cudaMemsetAsync(w.colinv, 0, sizeof(float) * SC * 8 * w.ci_pitch, st));
-    int rc = mf_energy(sh, d_data, w.colinv, nullptr, w.ci_pitch, true, true, st);
+    BPMF_CUDA(cudaMemsetAsync(w.colinv, 0, sizeof(float) * SC * w.ci_pitch, st));
+    int rc = mf_energy(sh, d_data, w.colinv + TC_FRONT, nullptr, w.ci_pitch, true, false, st);
     if (rc != BPMF_OK) return rc;
     // templates: resident A images + per-row constants
     tc_template_prep_kernel<<<dim3((unsigned)w.MT, (unsigned)SC), TC_ROWS, 0, st>>>(
@@ -618,6 +624,10 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     p.n_tiles = w.n_tiles;
     p.seg_tiles = TC_SEG_TILES;
     p.n_seg = (w.n_tiles + TC_SEG_TILES - 1) / TC_SEG_TILES;
+    {
+        const char *dbg = getenv("BPMF_TC_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
     const long long n_items = (long long)p.n_seg * p.MT * p.SC * p.n_kc;
     BPMF_REQUIRE(n_items < (1ll << 31), "matched filter: too many work items for the tensor path");
     BPMF_CUDA(cudaFuncSetAttribute(mf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bytes));

@@ -52,6 +52,41 @@ __global__ void st_v4_rows(float* out, size_t pitch, int rows, int cols, int ite
     }
 }
 
+// pattern E: warp = 1 row x 32 consecutive floats (one full 128-byte line per warp op)
+__global__ void red_line(float* out, size_t pitch, int rows, int cols, int iters) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int r = warp % rows;
+    for (int it = 0; it < iters; it++) {
+        float* p = out + (size_t)r * pitch + (size_t)((it * 977 + warp / rows) % (cols / 32 - 32)) * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < 32; u++) atomicAdd(p + u * 32, 1.0f);
+    }
+}
+// pattern F: warp = 1 row, 4 sectors alternating over 2 lines (lane group g -> sector 2g), as the
+// 16x256b TMEM load shape would give
+__global__ void red_alt(float* out, size_t pitch, int rows, int cols, int iters) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int r = warp % rows;
+    for (int it = 0; it < iters; it++) {
+        float* p = out + (size_t)r * pitch + (size_t)((it * 977 + warp / rows) % (cols / 64 - 32)) * 64 + (lane >> 3) * 16 + (lane & 7);
+#pragma unroll
+        for (int u = 0; u < 32; u++) atomicAdd(p + (u >> 1) * 64 + (u & 1) * 8, 1.0f);
+    }
+}
+// pattern G: red.v4, 8 lanes per 128-byte line, 4 rows per warp op (512 B per op)
+__global__ void red_v4_line(float* out, size_t pitch, int rows, int cols, int iters) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int r = (warp * 4 + (lane >> 3)) % rows;
+    for (int it = 0; it < iters; it++) {
+        float* p = out + (size_t)r * pitch + (size_t)((it * 977 + warp / (rows / 4)) % (cols / 32 - 32)) * 32 + (lane & 7) * 4;
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+            float* q = p + u * 32;
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(1.f), "f"(1.f), "f"(1.f), "f"(1.f) : "memory");
+        }
+    }
+}
+
 template <typename F>
 void run(const char* name, F launch, double elems_per_launch) {
     cudaEvent_t a, b;
@@ -69,13 +104,16 @@ int main() {
     const int rows = 512, cols = 16384;  // 32 MB working set: L2 resident
     const size_t pitch = cols;
     float* out; cudaMalloc(&out, sizeof(float) * rows * pitch); cudaMemset(out, 0, sizeof(float) * rows * pitch);
-    for (int threads : {128, 256, 512}) {
+    for (int threads : {256}) {
         const int blocks = 148, iters = 64;
         const double warps = blocks * threads / 32.0;
         printf("--- %d CTAs x %d threads\n", blocks, threads);
         run("red.f32 4x8", [&] { red_scalar<<<blocks, threads>>>(out, pitch, rows, cols, iters); }, warps * iters * 32 * 32);
         run("red.v4 16x8", [&] { red_v4<<<blocks, threads>>>(out, pitch, rows, cols, iters); }, warps * iters * 32 * 128);
         run("red.v4 32x4", [&] { red_v4_rows<<<blocks, threads>>>(out, pitch, rows, cols, iters); }, warps * iters * 32 * 128);
+        run("red.f32 1x32", [&] { red_line<<<blocks, threads>>>(out, pitch, rows, cols, iters); }, warps * iters * 32 * 32);
+        run("red.f32 alt", [&] { red_alt<<<blocks, threads>>>(out, pitch, rows, cols, iters); }, warps * iters * 32 * 32);
+        run("red.v4 4x32", [&] { red_v4_line<<<blocks, threads>>>(out, pitch, rows, cols, iters); }, warps * iters * 32 * 128);
         run("st.v4 32x4", [&] { st_v4_rows<<<blocks, threads>>>(out, pitch, rows, cols, iters); }, warps * iters * 32 * 128);
     }
     return 0;
