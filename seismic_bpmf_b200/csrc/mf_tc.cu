@@ -175,28 +175,58 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// one 32-column chunk of the epilogue: TMEM -> registers -> normalise -> red.global.add
-// mode 2: every lane's 128 columns are valid; 1: per-column predicate; 0: nothing to write.
-// inv points at this row's first rsqrt(energy) value of the chunk; column c lives 8*c floats on.
-__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, float *dst, int c0, int c_lo,
-                                             int c_hi, int mode, float ithr, float scale, int debug) {
+// 4x4 transpose between the template index of a lane (lane >> 3) and the column index within a
+// group of four registers, by two butterfly exchanges.  Before: lane (a, r), register x = template a,
+// column 4g+x.  After: lane (a, r), register x = template x, column 4g+a -- so register x of the 32
+// lanes is 32 CONSECUTIVE outputs (offset 8*(4g+a) + r = 32g + lane) of template x.
+__device__ __forceinline__ void tc_transpose4(float &v0, float &v1, float &v2, float &v3, bool b16, bool b8) {
+    {   // exchange across lane bit 16 <-> register bit 1: pairs (0,2) and (1,3)
+        float s0 = b16 ? v0 : v2, s1 = b16 ? v1 : v3;
+        s0 = __shfl_xor_sync(0xffffffffu, s0, 16);
+        s1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+        if (b16) { v0 = s0; v1 = s1; } else { v2 = s0; v3 = s1; }
+    }
+    {   // exchange across lane bit 8 <-> register bit 0: pairs (0,1) and (2,3)
+        float s0 = b8 ? v0 : v1, s1 = b8 ? v2 : v3;
+        s0 = __shfl_xor_sync(0xffffffffu, s0, 8);
+        s1 = __shfl_xor_sync(0xffffffffu, s1, 8);
+        if (b8) { v0 = s0; v2 = s1; } else { v1 = s0; v3 = s1; }
+    }
+}
+
+// one 32-column chunk of the epilogue: TMEM -> registers -> normalise -> transpose -> red.global.add
+// in whole 128-byte runs.  inv points at this row's first rsqrt(energy) value of the chunk (column c
+// lives 8*c floats on); base[x] points at output 8*(first column of the chunk - q_x) + lane of the
+// warp's x-th template; i0[x] is that output's index, valid iff lo[x] <= i <= hi[x].
+// mode 2: everything valid; 1: per-element predicate; 0: nothing to write.
+__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, float *const (&base)[4],
+                                             const int (&i0)[4], const int (&lo)[4], const int (&hi)[4], int mode,
+                                             float ithr, float scale, bool b16, bool b8, int debug) {
     float v[32];
     tc_ld32(taddr, v);
     if (debug & 1) mode = (v[0] == 12345.678f) ? mode : 0;  // triage: keep everything but the reductions
+    if (mode == 0) return;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        const float w = inv[8 * c];
+        const float x = v[c] * w;
+        v[c] = (w < ithr) ? x * scale : 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++) tc_transpose4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], b16, b8);
     if (mode == 2) {
 #pragma unroll
-        for (int c = 0; c < 32; c++) {
-            const float w = inv[8 * c];
-            const float x = v[c] * w;
-            atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
-        }
-    } else if (mode == 1) {
+        for (int g = 0; g < 8; g++)
 #pragma unroll
-        for (int c = 0; c < 32; c++) {
-            const float w = inv[8 * c];
-            const float x = v[c] * w;
-            if (c0 + c >= c_lo && c0 + c < c_hi) atomicAdd(dst + 8 * c, (w < ithr) ? x * scale : 0.f);
-        }
+            for (int x = 0; x < 4; x++) atomicAdd(base[x] + 32 * g, v[4 * g + x]);
+    } else {
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int i = i0[x] + 32 * g;
+                if (i >= lo[x] && i <= hi[x]) atomicAdd(base[x] + 32 * g, v[4 * g + x]);
+            }
     }
 }
 
@@ -372,7 +402,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 jj_lo = (long long)((a >= 0) ? (a + 7) / 8 : -((-a) / 8)) + q;  // ceil(a / 8) + q
                 jj_hi = (long long)((b >= 0) ? b / 8 : -((-b + 7) / 8)) + q;    // floor(b / 8) + q
             }
-            float *out_row = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + ir;
+            // the warp's four templates after the transpose: row base, column shift, valid range
+            float *tbase[4];
+            int tq[4], tlo[4], thi[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int tx = mt * TC_TPL + quarter * 4 + x;
+                const size_t mr = (size_t)(ch * p.MT + mt) * TC_ROWS + quarter * 32 + 8 * x;
+                tq[x] = p.row_q[mr];
+                const bool live = tx < p.T && p.row_scale[mr] != 0.f;
+                tlo[x] = live ? p.lo[tx] : 1;
+                thi[x] = live ? p.hi[tx] : 0;
+                tbase[x] = p.cc + (size_t)(tx < p.T ? tx : 0) * p.cc_pitch + lane;
+            }
+            const bool b16 = (lane & 16) != 0, b8 = (lane & 8) != 0;
             const int t_begin = seg * p.seg_tiles;
             const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
             for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
@@ -387,15 +430,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 const int c_hi = (int)(c_hi64 > 128 ? 128 : (c_hi64 < 0 ? 0 : c_hi64));
                 const int mode = __all_sync(0xffffffffu, c_lo == 0 && c_hi == 128)
                                      ? 2 : (__any_sync(0xffffffffu, c_hi > c_lo) ? 1 : 0);
-                float *dst = out_row + 8 * (jj0 - q);
 #pragma unroll 1
                 for (int chunk = 0; chunk < 4; chunk++, n_chunk++) {
                     const int slot = n_chunk % TC_NI;
                     uint64_t *full = inv_full + half * TC_NI + slot;
                     mbar_wait(full, (n_chunk / TC_NI) & 1);
                     const float *inv = inv_s + (half * TC_NI + slot) * TC_INV_SLOT + e;
-                    tc_epi_chunk(taddr + (uint32_t)(chunk * 32), inv, dst + 8 * (chunk * 32), chunk * 32, c_lo, c_hi,
-                                 mode, ithr, scale, p.debug);
+                    float *cbase[4];
+                    int ci0[4];
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const long long o = 8 * (jj0 + chunk * 32 - tq[x]);  // output index of lane 0, register group 0
+                        cbase[x] = tbase[x] + o;
+                        ci0[x] = (int)(o + lane);
+                    }
+                    tc_epi_chunk(taddr + (uint32_t)(chunk * 32), inv, cbase, ci0, tlo, thi, mode, ithr, scale, b16, b8,
+                                 p.debug);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(inv_empty + half * TC_NI + slot);
                 }
