@@ -112,3 +112,18 @@ def test_host_helper_symbols():
     m = lib._compute_average(a.ctypes.data_as(fp), a.size)
     assert abs(m - a.mean()) < 1e-6
     assert abs(lib._compute_std(a.ctypes.data_as(fp), m, a.size) - a.std()) < 1e-6
+
+
+def test_reference_clib_py_loads_against_this_library():
+    """The reference's own BPMF/clib.py (unchanged) binds every symbol it needs from libbpmf_b200.so
+    installed as lib/libc.so (only where /root/reference exists; compute calls need a GPU)."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("/root/reference is not present on this box")
+    pkg_dir = os.path.dirname(os.path.dirname(build.lib_path()))  # .../seismic_bpmf_b200 holds lib/libc.so
+    clib_ref = ref_loader.load_reference_clib(package_dir=pkg_dir)
+    assert clib_ref.cpu_loaded
+    for sym in ("kurtosis", "find_similar_moveouts", "find_similar_moveouts2", "select_cc_indexes",
+                "time_dependent_threshold"):
+        assert getattr(clib_ref._libc, sym).argtypes is not None
