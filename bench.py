@@ -168,7 +168,7 @@ def cpu_sample_throughput(seconds, S, Cc, L, seed=SEED):
         mv = rng.integers(0, min(3000, N // 8) + 1, (T, S, Cc)).astype(np.int32)
         w = np.full((T, S, Cc), 1.0 / (S * Cc), np.float32)
         t0 = time.perf_counter()
-        cc = cpu.matched_filter(tp, mv, w, data, 1)
+        cc = cpu.matched_filter(tp, mv, w, data, 1, num_threads=cores)  # torchrun exports OMP_NUM_THREADS=1
         dt = time.perf_counter() - t0
         return T * S * Cc * cc.shape[1] / dt / 1e9, dt
 
@@ -231,23 +231,33 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:  # traces are replicated: take rank 0's
         dist.broadcast(data, src=0)
         planted = {}
-    plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, precision=args.precision, device=device)
+    # N > 1: the per-rank pass runs in template batches so that the all-gather of one batch's CC slab
+    # overlaps the kernels of the next one
+    batch = T if world == 1 else 128
+    plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, precision=args.precision, device=device, batch=batch)
     n_corr = plan.n_corr
     units = T * S * Cc * n_corr  # per rank, per step
 
-    gather_rows = 25
-    gbuf = None
+    gbufs = None
     if world > 1:
-        gbuf = torch.empty(world * gather_rows * plan.pitch, dtype=torch.float32, device=device)
+        gbufs = [torch.empty(world * batch * plan.pitch, dtype=torch.float32, device=device) for _ in range(2)]
 
     def step_fn():
-        cc = plan.run(tp, mv, w, data)
-        if world > 1:  # the exchange step: chunked all-gather of the per-shard CC slab
-            for t0 in range(0, T, gather_rows):
-                rows = min(gather_rows, T - t0)
-                src = plan.cc[t0: t0 + rows].reshape(-1)
-                dist.all_gather_into_tensor(gbuf[: world * rows * plan.pitch], src)
-        return cc
+        if world == 1:
+            return plan.run(tp, mv, w, data)
+        plan.prepare(data)
+        works = []
+        for b, t0 in enumerate(range(0, T, batch)):
+            rows = min(batch, T - t0)
+            plan.run_batch(tp, mv, w, data, t0)
+            if b >= 2:
+                works[b - 2].wait()  # the gather buffer about to be reused is free again
+            # the exchange step: NCCL all-gather of this batch's per-shard CC slab (runs on NCCL's stream)
+            works.append(dist.all_gather_into_tensor(gbufs[b % 2][: world * rows * plan.pitch],
+                                                     plan.cc[t0: t0 + rows].reshape(-1), async_op=True))
+        for wk in works:
+            wk.wait()
+        return plan.cc
 
     for _ in range(args.warmup):
         step_fn()
@@ -309,8 +319,7 @@ def run_ours(args, rank, world, local_rank):
         h2d = sum(h[k].nbytes for k in h)
         d2h = out_np.nbytes
         del plan  # the host entry point allocates its own device buffers
-        if gbuf is not None:
-            del gbuf
+        gbufs = None
         torch.cuda.empty_cache()
         fmf.matched_filter(h["tp"], h["mv"], h["w"], h["data"], step, arch="gpu", precision=args.precision,
                            check_zeros=False, out=out_np)  # warm-up
@@ -365,7 +374,8 @@ def run_ours(args, rank, world, local_rank):
                    % (T, S, Cc, L, N), "precision": prec_name, "templates_total": T * world,
                    "l2": "inputs (%.2f GB) and output (%.2f GB) exceed the 126 MB L2" % (
                        (data.numel() * 4 + tp.numel() * 4) / 1e9, T * n_corr * 4 / 1e9),
-                   "collective": "chunked NCCL all-gather of per-shard CC slabs" if world > 1 else "none"},
+                   "collective": ("NCCL all-gather of per-shard CC slabs, one per 128-template batch, overlapped "
+                                  "with the next batch's kernels") if world > 1 else "none"},
         "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "parity": parity,
     }

@@ -89,6 +89,30 @@ int bpmf_matched_filter_dev(const float *d_templates, const int *d_moveouts,
                             size_t n_stations, size_t n_components, int normalize,
                             int network_sum, int precision, void *d_workspace,
                             size_t workspace_bytes, float *d_cc, size_t cc_pitch, void *stream);
+/* The same work in two steps, for callers that run many template batches against the same traces
+ * (BPMF/similarity_search.py:783-790 loops template chunks over one day of data): the trace-side
+ * staging (fp16 copies, window energies) is prepared once into `d_trace_ws` and reused, read-only,
+ * by every bpmf_mf_run_dev call -- also concurrently from several streams, each with its own
+ * `d_template_ws`.  L, N, S, C, step, normalize, network_sum and precision must match. */
+size_t bpmf_mf_trace_workspace_bytes(size_t n_samples_template, size_t n_samples_data, size_t n_stations,
+                                     size_t n_components, size_t step, int normalize, int network_sum,
+                                     int precision);
+size_t bpmf_mf_template_workspace_bytes(size_t n_samples_template, size_t n_samples_data,
+                                        size_t n_templates, size_t n_stations, size_t n_components,
+                                        size_t step, int normalize, int network_sum, int precision);
+int bpmf_mf_prepare_traces_dev(const float *d_data, size_t step, size_t n_samples_template,
+                               size_t n_samples_data, size_t n_stations, size_t n_components,
+                               int normalize, int network_sum, int precision, void *d_trace_ws,
+                               size_t trace_ws_bytes, void *stream);
+int bpmf_mf_run_dev(const float *d_templates, const int *d_moveouts, const float *d_weights,
+                    const float *d_data, size_t step, size_t n_samples_template, size_t n_samples_data,
+                    size_t n_templates, size_t n_stations, size_t n_components, int normalize,
+                    int network_sum, int precision, void *d_trace_ws, size_t trace_ws_bytes,
+                    void *d_template_ws, size_t template_ws_bytes, float *d_cc, size_t cc_pitch,
+                    void *stream);
+/* frees the device buffers the host-pointer entry points keep cached on the current device */
+void bpmf_release_cache(void);
+
 /* Shape-only check of a precision selector: returns the arithmetic it maps to, or a negative value
  * when it is not available for the shape.  For BPMF_MF_AUTO this is the fastest arithmetic the
  * shape allows; the call itself inspects the weights (4 bytes read back, the one host

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -63,21 +64,25 @@ static MfShape make_shape(size_t L, size_t N, size_t T, size_t S, size_t C, size
     return sh;
 }
 
-struct MfWs {
-    MfMeta meta;
+// fp32 path staging: window energy (+ mean) per channel on the trace side, template statistics and
+// bounds on the template side
+struct MfTraceWs {
     float *energy, *mean;
 };
-
-static MfWs carve_fp32(Workspace &ws, const MfShape &sh) {
-    MfWs w;
-    w.meta.sst = ws.take<float>(sh.T * sh.SC());
-    w.meta.sumt = ws.take<float>(sh.T * sh.SC());
-    w.meta.lo = ws.take<int>(sh.T);
-    w.meta.hi = ws.take<int>(sh.T);
+static MfTraceWs carve_fp32_traces(Workspace &ws, const MfShape &sh) {
+    MfTraceWs w;
     const size_t n_win = sh.N >= sh.L ? sh.N - sh.L + 1 : 0;
     w.energy = ws.take<float>(sh.SC() * n_win);
     w.mean = sh.normalize ? ws.take<float>(sh.SC() * n_win) : nullptr;
     return w;
+}
+static MfMeta carve_meta(Workspace &ws, const MfShape &sh) {
+    MfMeta m;
+    m.sst = ws.take<float>(sh.T * sh.SC());
+    m.sumt = ws.take<float>(sh.T * sh.SC());
+    m.lo = ws.take<int>(sh.T);
+    m.hi = ws.take<int>(sh.T);
+    return m;
 }
 
 // Shape-only resolution: for AUTO this is the FASTEST arithmetic the shape allows; the call itself
@@ -187,23 +192,95 @@ extern "C" int bpmf_mf_resolve_precision(size_t L, size_t step, int normalize, i
     return resolve_precision(sh, precision);
 }
 
-extern "C" size_t bpmf_mf_workspace_bytes(size_t L, size_t N, size_t T, size_t S, size_t C,
-                                          size_t step, int normalize, int network_sum,
-                                          int precision) {
+static bool is_tc(int prec) { return prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3; }
+// the split arithmetic needs the residual (lo) traces; AUTO may pick it at run time
+static bool wants_lo(int precision) { return precision == BPMF_MF_TC_FP16X3 || precision == BPMF_MF_AUTO; }
+
+extern "C" size_t bpmf_mf_trace_workspace_bytes(size_t L, size_t N, size_t S, size_t C, size_t step,
+                                                int normalize, int network_sum, int precision) {
+    MfShape sh = make_shape(L, N, 1, S, C, step, normalize, network_sum);
+    const int prec = resolve_precision(sh, precision);
+    if (is_tc(prec)) return mf_tc_trace_ws_bytes(sh, wants_lo(precision));
+    Workspace ws(nullptr, 0);
+    carve_fp32_traces(ws, sh);
+    return ws.used;
+}
+
+extern "C" size_t bpmf_mf_template_workspace_bytes(size_t L, size_t N, size_t T, size_t S, size_t C,
+                                                   size_t step, int normalize, int network_sum,
+                                                   int precision) {
     MfShape sh = make_shape(L, N, T, S, C, step, normalize, network_sum);
     const int prec = resolve_precision(sh, precision);
     Workspace ws(nullptr, 0);
-    if (prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3) {
-        ws.take<float>(sh.T * sh.SC());
-        ws.take<float>(sh.T * sh.SC());
-        ws.take<int>(sh.T);
-        ws.take<int>(sh.T);
-        size_t need = mf_tc_workspace_bytes(sh, prec == BPMF_MF_TC_FP16X3);
-        if (precision == BPMF_MF_AUTO) need = std::max(need, mf_tc_workspace_bytes(sh, 1));  // AUTO may split
+    ws.take<float>(64);  // scratch of the AUTO policy
+    carve_meta(ws, sh);
+    if (is_tc(prec)) {
+        size_t need = mf_tc_template_ws_bytes(sh, prec == BPMF_MF_TC_FP16X3);
+        if (precision == BPMF_MF_AUTO) need = std::max(need, mf_tc_template_ws_bytes(sh, 1));
         return ws.used + need;
     }
-    carve_fp32(ws, sh);
     return ws.used;
+}
+
+extern "C" size_t bpmf_mf_workspace_bytes(size_t L, size_t N, size_t T, size_t S, size_t C,
+                                          size_t step, int normalize, int network_sum,
+                                          int precision) {
+    return align_up(bpmf_mf_trace_workspace_bytes(L, N, S, C, step, normalize, network_sum, precision), 256) +
+           bpmf_mf_template_workspace_bytes(L, N, T, S, C, step, normalize, network_sum, precision);
+}
+
+extern "C" int bpmf_mf_prepare_traces_dev(const float *d_data, size_t step, size_t L, size_t N, size_t S,
+                                          size_t C, int normalize, int network_sum, int precision,
+                                          void *d_trace_ws, size_t trace_ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    BPMF_REQUIRE(step >= 1 && L >= 1 && S >= 1 && C >= 1, "matched_filter: empty shape");
+    BPMF_REQUIRE(N >= L, "matched_filter: data (%zu) shorter than template (%zu)", N, L);
+    BPMF_REQUIRE(N < ((size_t)1 << 31), "matched_filter: n_samples_data exceeds int32 indexing");
+    MfShape sh = make_shape(L, N, 1, S, C, step, normalize ? 1 : 0, network_sum ? 1 : 0);
+    const int prec = resolve_precision(sh, precision);
+    BPMF_REQUIRE(prec > 0, "matched_filter: precision %d is not available for L=%zu step=%zu "
+                 "normalize=%d network_sum=%d", precision, L, step, normalize, network_sum);
+    Workspace ws(d_trace_ws, trace_ws_bytes);
+    if (is_tc(prec)) return mf_tc_prepare_traces(sh, wants_lo(precision), d_data, ws, st);
+    MfTraceWs w = carve_fp32_traces(ws, sh);
+    BPMF_REQUIRE(ws.ok(), "matched_filter: trace workspace too small (%zu < %zu)", trace_ws_bytes, ws.used);
+    return mf_energy(sh, d_data, w.energy, w.mean, sh.N - sh.L + 1, false, false, st);
+}
+
+extern "C" int bpmf_mf_run_dev(const float *d_templates, const int *d_moveouts, const float *d_weights,
+                               const float *d_data, size_t step, size_t L, size_t N, size_t T, size_t S,
+                               size_t C, int normalize, int network_sum, int precision, void *d_trace_ws,
+                               size_t trace_ws_bytes, void *d_template_ws, size_t template_ws_bytes,
+                               float *d_cc, size_t cc_pitch, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    BPMF_REQUIRE(step >= 1 && L >= 1 && S >= 1 && C >= 1, "matched_filter: empty shape");
+    BPMF_REQUIRE(N >= L, "matched_filter: data (%zu) shorter than template (%zu)", N, L);
+    if (T == 0) return BPMF_OK;
+    MfShape sh = make_shape(L, N, T, S, C, step, normalize ? 1 : 0, network_sum ? 1 : 0);
+    BPMF_REQUIRE(!sh.network_sum || cc_pitch >= sh.n_corr, "matched_filter: cc_pitch < n_corr");
+    int prec = resolve_precision(sh, precision);
+    BPMF_REQUIRE(prec > 0, "matched_filter: precision %d is not available for L=%zu step=%zu "
+                 "normalize=%d network_sum=%d", precision, L, step, normalize, network_sum);
+    BPMF_REQUIRE(d_trace_ws && d_template_ws, "matched_filter: workspace missing");
+    Workspace tws(d_trace_ws, trace_ws_bytes), pws(d_template_ws, template_ws_bytes);
+    float *scratch = pws.take<float>(64);
+    MfMeta meta = carve_meta(pws, sh);
+    BPMF_REQUIRE(pws.ok(), "matched_filter: template workspace too small");
+    int rc;
+    if (precision == BPMF_MF_AUTO && prec == BPMF_MF_TC_FP16) {
+        // the only host synchronisation of this entry point: 4 bytes of weight statistics
+        if ((rc = mf_auto_precision(sh, d_weights, scratch, st, &prec)) != BPMF_OK) return rc;
+    }
+    g_last_precision = prec;
+    if ((rc = mf_prepass(sh, d_templates, d_moveouts, d_weights, d_data, meta, nullptr, nullptr, st)) != BPMF_OK)
+        return rc;
+    if (is_tc(prec))
+        return mf_tc_run(sh, prec == BPMF_MF_TC_FP16X3, d_templates, d_moveouts, d_weights, meta, tws,
+                         wants_lo(precision), pws, d_cc, cc_pitch, st);
+    MfTraceWs w = carve_fp32_traces(tws, sh);
+    BPMF_REQUIRE(tws.ok(), "matched_filter: trace workspace too small");
+    if (!sh.network_sum) BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * sh.n_corr * sh.SC(), st));
+    return mf_fp32_run(sh, d_templates, d_moveouts, d_weights, d_data, meta, w.energy, w.mean, d_cc, cc_pitch, st);
 }
 
 extern "C" int bpmf_matched_filter_dev(const float *d_templates, const int *d_moveouts,
@@ -212,53 +289,64 @@ extern "C" int bpmf_matched_filter_dev(const float *d_templates, const int *d_mo
                                        int normalize, int network_sum, int precision,
                                        void *d_workspace, size_t workspace_bytes, float *d_cc,
                                        size_t cc_pitch, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    BPMF_REQUIRE(step >= 1 && L >= 1 && S >= 1 && C >= 1, "matched_filter: empty shape");
-    BPMF_REQUIRE(N >= L, "matched_filter: data (%zu) shorter than template (%zu)", N, L);
-    BPMF_REQUIRE(N < ((size_t)1 << 31), "matched_filter: n_samples_data exceeds int32 indexing");
     if (T == 0) return BPMF_OK;
-    MfShape sh = make_shape(L, N, T, S, C, step, normalize ? 1 : 0, network_sum ? 1 : 0);
-    BPMF_REQUIRE(!sh.network_sum || cc_pitch >= sh.n_corr, "matched_filter: cc_pitch < n_corr");
-    int prec = resolve_precision(sh, precision);
-    BPMF_REQUIRE(prec > 0, "matched_filter: precision %d is not available for L=%zu step=%zu "
-                 "normalize=%d network_sum=%d", precision, L, step, normalize, network_sum);
-    BPMF_REQUIRE(workspace_bytes >= 256 && d_workspace != nullptr, "matched_filter: workspace missing");
-    Workspace ws(d_workspace, workspace_bytes);
-    int rc;
-    if (precision == BPMF_MF_AUTO && prec == BPMF_MF_TC_FP16) {
-        // the only host synchronisation of this entry point: 4 bytes of weight statistics
-        if ((rc = mf_auto_precision(sh, d_weights, (float *)d_workspace, st, &prec)) != BPMF_OK) return rc;
-    }
-    g_last_precision = prec;
-    if (prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3) {
-        MfMeta meta;
-        meta.sst = ws.take<float>(sh.T * sh.SC());
-        meta.sumt = ws.take<float>(sh.T * sh.SC());
-        meta.lo = ws.take<int>(sh.T);
-        meta.hi = ws.take<int>(sh.T);
-        BPMF_REQUIRE(ws.used + mf_tc_workspace_bytes(sh, prec == BPMF_MF_TC_FP16X3) <= workspace_bytes,
-                     "matched_filter: workspace too small");
-        if ((rc = mf_prepass(sh, d_templates, d_moveouts, d_weights, d_data, meta, nullptr, nullptr,
-                             st)) != BPMF_OK)
-            return rc;
-        return mf_tc_run(sh, prec == BPMF_MF_TC_FP16X3, d_templates, d_moveouts, d_weights, d_data,
-                         meta, ws, d_cc, cc_pitch, st);
-    }
-    MfWs w = carve_fp32(ws, sh);
-    BPMF_REQUIRE(ws.ok(), "matched_filter: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
-    if ((rc = mf_prepass(sh, d_templates, d_moveouts, d_weights, d_data, w.meta, w.energy, w.mean,
-                         st)) != BPMF_OK)
-        return rc;
-    if (!sh.network_sum) {
-        BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * sh.n_corr * sh.SC(), st));
-    }
-    return mf_fp32_run(sh, d_templates, d_moveouts, d_weights, d_data, w.meta, w.energy, w.mean, d_cc,
-                       cc_pitch, st);
+    const size_t tb = align_up(bpmf_mf_trace_workspace_bytes(L, N, S, C, step, normalize, network_sum, precision), 256);
+    const size_t pb = bpmf_mf_template_workspace_bytes(L, N, T, S, C, step, normalize, network_sum, precision);
+    BPMF_REQUIRE(d_workspace && workspace_bytes >= tb + pb, "matched_filter: workspace too small (%zu < %zu)",
+                 workspace_bytes, tb + pb);
+    int rc = bpmf_mf_prepare_traces_dev(d_data, step, L, N, S, C, normalize, network_sum, precision, d_workspace,
+                                        tb, stream);
+    if (rc != BPMF_OK) return rc;
+    return bpmf_mf_run_dev(d_templates, d_moveouts, d_weights, d_data, step, L, N, T, S, C, normalize, network_sum,
+                           precision, d_workspace, tb, (char *)d_workspace + tb, pb, d_cc, cc_pitch, stream);
 }
 
-// Host-pointer entry point.  Data goes up once; templates are processed in chunks on two
-// streams so the device->host copy of one chunk's CC slab overlaps the next chunk's kernels
-// (the caller's buffers may be pinned -- then the copies are truly asynchronous -- or pageable).
+// ---------------------------------------------------------------- host-pointer entry point
+// Device buffers of the host path are cached per device (grow-only) so that the repeated calls BPMF makes
+// -- one per template chunk and per day of traces, BPMF/similarity_search.py:783-790 -- do not pay
+// cudaMalloc/cudaFree every time.  bpmf_release_cache() frees them.
+namespace bpmf {
+struct HostCache {
+    void *ptr[16] = {nullptr};
+    size_t cap[16] = {0};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr;
+    bool busy = false;
+};
+static HostCache g_cache[16];
+static std::mutex g_cache_mu;
+
+static cudaError_t cache_get(HostCache &c, int slot, size_t bytes, void **out) {
+    if (c.cap[slot] < bytes) {
+        if (c.ptr[slot]) cudaFree(c.ptr[slot]);
+        c.ptr[slot] = nullptr;
+        c.cap[slot] = 0;
+        cudaError_t e = cudaMalloc(&c.ptr[slot], bytes ? bytes : 1);
+        if (e != cudaSuccess) return e;
+        c.cap[slot] = bytes;
+    }
+    *out = c.ptr[slot];
+    return cudaSuccess;
+}
+static void cache_release(HostCache &c) {
+    for (int i = 0; i < 16; i++) {
+        if (c.ptr[i]) cudaFree(c.ptr[i]);
+        c.ptr[i] = nullptr;
+        c.cap[i] = 0;
+    }
+}
+}  // namespace bpmf
+
+extern "C" void bpmf_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return;
+    if (!g_cache[dev].busy) cache_release(g_cache[dev]);
+}
+
+// Traces go up and are staged once; templates are processed in chunks on two streams so the
+// device->host copy of one chunk's CC slab overlaps the next chunk's kernels (the caller's buffers
+// may be pinned -- then the copies are truly asynchronous -- or pageable).
 extern "C" int bpmf_matched_filter(const float *templates, const int *moveouts, const float *weights,
                                    const float *data, size_t step, size_t L, size_t N, size_t T,
                                    size_t S, size_t C, int normalize, int network_sum, int precision,
@@ -271,32 +359,32 @@ extern "C" int bpmf_matched_filter(const float *templates, const int *moveouts, 
     const size_t pitch = network_sum ? align_up(n_corr, 64) : 0;
     const size_t row_elems = network_sum ? pitch : n_corr * SC;
 
-    DevBuf d_data;
-    BPMF_CUDA(d_data.alloc(sizeof(float) * SC * N));
-    size_t free_b = 0, total_b = 0;
-    BPMF_CUDA(cudaMemGetInfo(&free_b, &total_b));
-
-    // chunk size: >= 4 chunks for overlap when T is large, bounded by a third of the free memory
-    size_t Tc = T;
-    if (T >= 64) Tc = (T + 3) / 4;
-    auto need = [&](size_t tc) {
-        return 2 * (sizeof(float) * tc * row_elems + sizeof(float) * tc * SC * L + 8 * tc * SC) +
-               bpmf_mf_workspace_bytes(L, N, tc, S, C, step, normalize, network_sum, precision);
-    };
-    while (Tc > 1 && need(Tc) > free_b / 3 * 2) Tc = (Tc + 1) / 2;
-    BPMF_REQUIRE(need(Tc) <= free_b, "matched_filter: not enough device memory (%zu needed, %zu free)",
-                 need(Tc), free_b);
-    if (network_sum && Tc >= 32) Tc = Tc / 16 * 16;  // whole tensor-path template tiles per chunk
-    const size_t ws_bytes = bpmf_mf_workspace_bytes(L, N, Tc, S, C, step, normalize, network_sum, precision);
-
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t ev_data = nullptr;
-    DevBuf d_tp[2], d_mv[2], d_w[2], d_cc[2], d_ws[2];
+    int dev = 0;
+    BPMF_CUDA(cudaGetDevice(&dev));
+    // one host-path call at a time per device uses the cache; a concurrent caller gets private buffers
+    HostCache local;
+    HostCache *c = &local;
+    bool cached = false;
+    if (dev >= 0 && dev < 16) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (!g_cache[dev].busy) {
+            g_cache[dev].busy = true;
+            c = &g_cache[dev];
+            cached = true;
+        }
+    }
     int rc = BPMF_OK;
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; i++)
-            if (st[i]) cudaStreamDestroy(st[i]);
-        if (ev_data) cudaEventDestroy(ev_data);
+    auto finish = [&](int code) {
+        if (cached) {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            c->busy = false;
+        } else {
+            cache_release(local);
+            for (int i = 0; i < 2; i++)
+                if (local.st[i]) cudaStreamDestroy(local.st[i]);
+            if (local.ev) cudaEventDestroy(local.ev);
+        }
+        return code;
     };
 #define MF_TRY(expr)                                                                        \
     do {                                                                                    \
@@ -304,57 +392,83 @@ extern "C" int bpmf_matched_filter(const float *templates, const int *moveouts, 
         if (_e != cudaSuccess) {                                                            \
             set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
             cudaDeviceSynchronize();                                                        \
-            cleanup();                                                                      \
-            return BPMF_E_CUDA;                                                             \
+            cudaGetLastError();                                                             \
+            return finish(BPMF_E_CUDA);                                                     \
         }                                                                                   \
     } while (0)
-    const int n_buf = (Tc < T) ? 2 : 1;
-    for (int i = 0; i < n_buf; i++) {
-        MF_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-        MF_TRY(d_tp[i].alloc(sizeof(float) * Tc * SC * L));
-        MF_TRY(d_mv[i].alloc(sizeof(int) * Tc * SC));
-        MF_TRY(d_w[i].alloc(sizeof(float) * Tc * SC));
-        MF_TRY(d_cc[i].alloc(sizeof(float) * Tc * row_elems));
-        MF_TRY(d_ws[i].alloc(ws_bytes));
+    for (int i = 0; i < 2; i++)
+        if (!c->st[i]) MF_TRY(cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking));
+    if (!c->ev) MF_TRY(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+
+    const size_t trace_b = bpmf_mf_trace_workspace_bytes(L, N, S, C, step, normalize, network_sum, precision);
+    void *d_data = nullptr, *d_trace = nullptr;
+    MF_TRY(cache_get(*c, 0, sizeof(float) * SC * N, &d_data));
+    MF_TRY(cache_get(*c, 1, trace_b, &d_trace));
+    size_t free_b = 0, total_b = 0;
+    MF_TRY(cudaMemGetInfo(&free_b, &total_b));
+    for (int i = 2; i < 12; i++) free_b += c->cap[i];  // chunk buffers already held by the cache are reusable
+
+    // chunk size: ~8 chunks for overlap when T is large, bounded by half of the free memory
+    size_t Tc = T;
+    if (T >= 128) Tc = align_up((T + 7) / 8, 16);
+    auto need = [&](size_t tc) {
+        return 2 * (sizeof(float) * tc * row_elems + sizeof(float) * tc * SC * L + 8 * tc * SC +
+                    bpmf_mf_template_workspace_bytes(L, N, tc, S, C, step, normalize, network_sum, precision));
+    };
+    while (Tc > 16 && need(Tc) > free_b / 2) Tc = align_up(Tc / 2, 16);
+    while (Tc > 1 && need(Tc) > free_b / 2) Tc = (Tc + 1) / 2;
+    if (need(Tc) > free_b) {
+        set_error("matched_filter: not enough device memory (%zu needed, %zu free)", need(Tc), free_b);
+        return finish(BPMF_E_NOMEM);
     }
-    MF_TRY(cudaEventCreateWithFlags(&ev_data, cudaEventDisableTiming));
-    MF_TRY(cudaMemcpyAsync(d_data.p, data, sizeof(float) * SC * N, cudaMemcpyHostToDevice, st[0]));
-    MF_TRY(cudaEventRecord(ev_data, st[0]));
+    const size_t tpl_b = bpmf_mf_template_workspace_bytes(L, N, Tc, S, C, step, normalize, network_sum, precision);
+    const int n_buf = (Tc < T) ? 2 : 1;
+    void *d_tp[2], *d_mv[2], *d_w[2], *d_cc[2], *d_ws[2];
+    for (int i = 0; i < n_buf; i++) {
+        MF_TRY(cache_get(*c, 2 + 5 * i + 0, sizeof(float) * Tc * SC * L, &d_tp[i]));
+        MF_TRY(cache_get(*c, 2 + 5 * i + 1, sizeof(int) * Tc * SC, &d_mv[i]));
+        MF_TRY(cache_get(*c, 2 + 5 * i + 2, sizeof(float) * Tc * SC, &d_w[i]));
+        MF_TRY(cache_get(*c, 2 + 5 * i + 3, sizeof(float) * Tc * row_elems, &d_cc[i]));
+        MF_TRY(cache_get(*c, 2 + 5 * i + 4, tpl_b, &d_ws[i]));
+    }
+    MF_TRY(cudaMemcpyAsync(d_data, data, sizeof(float) * SC * N, cudaMemcpyHostToDevice, c->st[0]));
+    rc = bpmf_mf_prepare_traces_dev((const float *)d_data, step, L, N, S, C, normalize, network_sum, precision,
+                                    d_trace, trace_b, c->st[0]);
+    if (rc != BPMF_OK) { cudaDeviceSynchronize(); return finish(rc); }
+    MF_TRY(cudaEventRecord(c->ev, c->st[0]));
 
     size_t chunk = 0;
     for (size_t t0 = 0; t0 < T; t0 += Tc, chunk++) {
         const size_t tc = std::min(Tc, T - t0);
         const int b = (int)(chunk % n_buf);
-        cudaStream_t s = st[b];
-        if (chunk == 1) MF_TRY(cudaStreamWaitEvent(s, ev_data, 0));
-        MF_TRY(cudaMemcpyAsync(d_tp[b].p, templates + t0 * SC * L, sizeof(float) * tc * SC * L,
+        cudaStream_t s = c->st[b];
+        if (chunk == 1) MF_TRY(cudaStreamWaitEvent(s, c->ev, 0));
+        MF_TRY(cudaMemcpyAsync(d_tp[b], templates + t0 * SC * L, sizeof(float) * tc * SC * L,
                                cudaMemcpyHostToDevice, s));
-        MF_TRY(cudaMemcpyAsync(d_mv[b].p, moveouts + t0 * SC, sizeof(int) * tc * SC,
-                               cudaMemcpyHostToDevice, s));
-        MF_TRY(cudaMemcpyAsync(d_w[b].p, weights + t0 * SC, sizeof(float) * tc * SC,
-                               cudaMemcpyHostToDevice, s));
-        rc = bpmf_matched_filter_dev(d_tp[b].as<float>(), d_mv[b].as<int>(), d_w[b].as<float>(),
-                                     d_data.as<float>(), step, L, N, tc, S, C, normalize, network_sum,
-                                     precision, d_ws[b].p, ws_bytes, d_cc[b].as<float>(), pitch, s);
+        MF_TRY(cudaMemcpyAsync(d_mv[b], moveouts + t0 * SC, sizeof(int) * tc * SC, cudaMemcpyHostToDevice, s));
+        MF_TRY(cudaMemcpyAsync(d_w[b], weights + t0 * SC, sizeof(float) * tc * SC, cudaMemcpyHostToDevice, s));
+        rc = bpmf_mf_run_dev((const float *)d_tp[b], (const int *)d_mv[b], (const float *)d_w[b],
+                             (const float *)d_data, step, L, N, tc, S, C, normalize, network_sum, precision,
+                             d_trace, trace_b, d_ws[b], tpl_b, (float *)d_cc[b], pitch, s);
         if (rc != BPMF_OK) break;
         if (network_sum)
-            MF_TRY(cudaMemcpy2DAsync(cc_out + t0 * n_corr, sizeof(float) * n_corr, d_cc[b].p,
+            MF_TRY(cudaMemcpy2DAsync(cc_out + t0 * n_corr, sizeof(float) * n_corr, d_cc[b],
                                      sizeof(float) * pitch, sizeof(float) * n_corr, tc,
                                      cudaMemcpyDeviceToHost, s));
         else
-            MF_TRY(cudaMemcpyAsync(cc_out + t0 * row_elems, d_cc[b].p, sizeof(float) * tc * row_elems,
+            MF_TRY(cudaMemcpyAsync(cc_out + t0 * row_elems, d_cc[b], sizeof(float) * tc * row_elems,
                                    cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < n_buf; i++) {
-        cudaError_t e = cudaStreamSynchronize(st[i]);
+    for (int i = 0; i < 2; i++) {
+        cudaError_t e = cudaStreamSynchronize(c->st[i]);
         if (e != cudaSuccess && rc == BPMF_OK) {
             set_error("matched_filter: stream sync -> %s", cudaGetErrorString(e));
+            cudaGetLastError();
             rc = BPMF_E_CUDA;
         }
     }
-    cleanup();
 #undef MF_TRY
-    return rc;
+    return finish(rc);
 }
 
 // Upstream fast_matched_filter symbols [UPSTREAM-UNVERIFIED]: void return, errors reported on stderr.

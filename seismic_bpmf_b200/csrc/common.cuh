@@ -108,11 +108,14 @@ int mf_fp32_run(const MfShape &sh, const float *d_templates, const int *d_moveou
                 const float *d_weights, const float *d_data, MfMeta meta, const float *d_energy,
                 const float *d_mean, float *d_cc, size_t cc_pitch, cudaStream_t st);
 
-// tensor-core (tcgen05) path
+// tensor-core (tcgen05) path: trace staging is prepared once and shared by every template batch
 bool mf_tc_supported(size_t L, size_t step, int normalize, int network_sum);
-size_t mf_tc_workspace_bytes(const MfShape &sh, int split);
+size_t mf_tc_trace_ws_bytes(const MfShape &sh, bool want_lo);
+size_t mf_tc_template_ws_bytes(const MfShape &sh, int split);
+int mf_tc_prepare_traces(const MfShape &sh, bool want_lo, const float *d_data, Workspace &trace_ws,
+                         cudaStream_t st);
 int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int *d_moveouts,
-              const float *d_weights, const float *d_data, MfMeta meta, Workspace &ws,
+              const float *d_weights, MfMeta meta, Workspace &trace_ws, bool traces_have_lo, Workspace &tpl_ws,
               float *d_cc, size_t cc_pitch, cudaStream_t st);
 
 }  // namespace bpmf

@@ -575,48 +575,67 @@ __global__ void __launch_bounds__(TC_ROWS)
 }
 
 // ---------------------------------------------------------------- host side
-struct TcWs {
-    __half *dh, *dh_lo;
-    float *colinv;
-    uint8_t *aimg;
-    int *row_q, *row_e, *item_active;
-    float *row_scale, *row_ithr, *ch_scale;
-    unsigned *chmax;
-    size_t dh_pitch, ci_pitch;
-    int MT, n_kc, Kc, a_bytes, a_img_bytes, b_slice_bytes, b_stage_bytes, n_tiles;
-    size_t smem_bytes;
+// Tile geometry: depends on (L, N) and on the arithmetic (single pass / split), not on T.
+struct TcGeom {
+    int n_kc, Kc, a_bytes, a_img_bytes, b_slice_bytes, b_stage_bytes, n_tiles;
+    size_t smem_bytes, dh_pitch, ci_pitch;
 };
 
-static TcWs tc_carve(Workspace &ws, const MfShape &sh, int split) {
-    TcWs w;
+static TcGeom tc_geom(const MfShape &sh, int split) {
+    TcGeom g;
     const int Kp = (int)align_up(sh.L + 14, 16);  // template length + largest row delay
     const int kc_max = split ? TC_KC_MAX_SPLIT : TC_KC_MAX;
-    w.n_kc = (Kp + kc_max - 1) / kc_max;
-    w.Kc = (int)align_up((size_t)(Kp + w.n_kc - 1) / w.n_kc, 16);
-    w.a_img_bytes = TC_ROWS * w.Kc * 2;
-    w.a_bytes = w.a_img_bytes * (split ? 2 : 1);
-    w.b_slice_bytes = (8 * (TC_NCOL - 1) + w.Kc) * 2;
-    w.b_stage_bytes = (int)align_up((size_t)w.b_slice_bytes * (split ? 2 : 1), 128);
-    w.smem_bytes = (size_t)w.a_bytes + TC_NB * (size_t)w.b_stage_bytes + 2 * TC_NI * TC_INV_SLOT * 4 + 320;
-    w.MT = (int)((sh.T + TC_TPL - 1) / TC_TPL);
+    g.n_kc = (Kp + kc_max - 1) / kc_max;
+    g.Kc = (int)align_up((size_t)(Kp + g.n_kc - 1) / g.n_kc, 16);
+    g.a_img_bytes = TC_ROWS * g.Kc * 2;
+    g.a_bytes = g.a_img_bytes * (split ? 2 : 1);
+    g.b_slice_bytes = (8 * (TC_NCOL - 1) + g.Kc) * 2;
+    g.b_stage_bytes = (int)align_up((size_t)g.b_slice_bytes * (split ? 2 : 1), 128);
+    g.smem_bytes = (size_t)g.a_bytes + TC_NB * (size_t)g.b_stage_bytes + 2 * TC_NI * TC_INV_SLOT * 4 + 320;
     const size_t n_cols = (sh.N - sh.L + TC_FRONT) / 8 + 1;  // GEMM columns that can hold a valid window start
-    w.n_tiles = (int)((n_cols + TC_NCOL - 1) / TC_NCOL);
-    // last slice read: (n_tiles-1)*2048 + (n_kc-1)*Kc + 2040 + Kc
-    w.dh_pitch = align_up((size_t)w.n_tiles * (8 * TC_NCOL) + (size_t)w.n_kc * w.Kc + 64, 64);
-    if (w.dh_pitch < align_up(sh.N + TC_FRONT, 64)) w.dh_pitch = align_up(sh.N + TC_FRONT, 64);
-    w.ci_pitch = (size_t)w.n_tiles * (8 * TC_NCOL) + 64;
+    g.n_tiles = (int)((n_cols + TC_NCOL - 1) / TC_NCOL);
+    // last trace slice read ends at (n_tiles-1)*2048 + (n_kc-1)*Kc + 2040 + Kc; the bound below holds for both
+    // arithmetics so that one staged copy of the traces serves the single pass and the split
+    g.dh_pitch = align_up((size_t)g.n_tiles * (8 * TC_NCOL) + 2 * (size_t)Kp + 128, 64);
+    if (g.dh_pitch < align_up(sh.N + TC_FRONT, 64)) g.dh_pitch = align_up(sh.N + TC_FRONT, 64);
+    g.ci_pitch = (size_t)g.n_tiles * (8 * TC_NCOL) + 64;
+    return g;
+}
+
+// trace-side staging: depends only on the traces (and L) -- prepared once, shared by every template batch
+struct TcTraceWs {
+    __half *dh, *dh_lo;
+    float *colinv, *ch_scale;
+    unsigned *chmax;
+};
+static TcTraceWs tc_carve_traces(Workspace &ws, const MfShape &sh, const TcGeom &g, bool want_lo) {
+    TcTraceWs w;
     const size_t SC = sh.SC();
-    w.dh = ws.take<__half>(SC * w.dh_pitch);
-    w.dh_lo = split ? ws.take<__half>(SC * w.dh_pitch) : nullptr;
-    w.colinv = ws.take<float>(SC * w.ci_pitch);
-    w.aimg = ws.take<uint8_t>(SC * (size_t)w.MT * w.n_kc * w.a_bytes);
+    w.ch_scale = ws.take<float>(SC);
+    w.chmax = ws.take<unsigned>(SC);
+    w.colinv = ws.take<float>(SC * g.ci_pitch);
+    w.dh = ws.take<__half>(SC * g.dh_pitch);
+    w.dh_lo = want_lo ? ws.take<__half>(SC * g.dh_pitch) : nullptr;
+    return w;
+}
+
+// template-side staging of one batch of T templates
+struct TcTplWs {
+    uint8_t *aimg;
+    int *row_q, *row_e, *item_active;
+    float *row_scale, *row_ithr;
+    int MT;
+};
+static TcTplWs tc_carve_templates(Workspace &ws, const MfShape &sh, const TcGeom &g) {
+    TcTplWs w;
+    const size_t SC = sh.SC();
+    w.MT = (int)((sh.T + TC_TPL - 1) / TC_TPL);
+    w.aimg = ws.take<uint8_t>(SC * (size_t)w.MT * g.n_kc * g.a_bytes);
     w.row_q = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
     w.row_e = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
     w.row_scale = ws.take<float>(SC * (size_t)w.MT * TC_ROWS);
     w.row_ithr = ws.take<float>(SC * (size_t)w.MT * TC_ROWS);
     w.item_active = ws.take<int>(SC * (size_t)w.MT);
-    w.ch_scale = ws.take<float>(SC);
-    w.chmax = ws.take<unsigned>(SC);
     return w;
 }
 
@@ -624,67 +643,85 @@ bool mf_tc_supported(size_t L, size_t step, int normalize, int network_sum) {
     return step == 1 && normalize == 0 && network_sum != 0 && L >= 8 && L <= 65536;
 }
 
-size_t mf_tc_workspace_bytes(const MfShape &sh, int split) {
+size_t mf_tc_trace_ws_bytes(const MfShape &sh, bool want_lo) {
     Workspace ws(nullptr, 0);
-    tc_carve(ws, sh, split);
+    tc_carve_traces(ws, sh, tc_geom(sh, 0), want_lo);
     return ws.used;
 }
 
-int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int *d_moveouts,
-              const float *d_weights, const float *d_data, MfMeta meta, Workspace &ws, float *d_cc,
-              size_t cc_pitch, cudaStream_t st) {
+size_t mf_tc_template_ws_bytes(const MfShape &sh, int split) {
+    Workspace ws(nullptr, 0);
+    tc_carve_templates(ws, sh, tc_geom(sh, split));
+    return ws.used;
+}
+
+// traces: per-channel scale, fp16 copy (hi [+ lo]), rsqrt(window energy)
+int mf_tc_prepare_traces(const MfShape &sh, bool want_lo, const float *d_data, Workspace &trace_ws,
+                         cudaStream_t st) {
     BPMF_REQUIRE(mf_tc_supported(sh.L, sh.step, sh.normalize, sh.network_sum),
                  "matched filter: shape not supported by the tensor path");
-    TcWs w = tc_carve(ws, sh, split);
-    BPMF_REQUIRE(ws.ok(), "matched filter: workspace too small for the tensor path");
-    BPMF_REQUIRE(w.smem_bytes <= TC_SMEM_LIMIT, "matched filter: tensor-path tile exceeds shared memory");
+    const TcGeom g = tc_geom(sh, 0);
+    TcTraceWs w = tc_carve_traces(trace_ws, sh, g, want_lo);
+    BPMF_REQUIRE(trace_ws.ok(), "matched filter: trace workspace too small for the tensor path");
     const size_t SC = sh.SC();
     BPMF_REQUIRE(SC <= 65535, "matched filter: too many channels");
-
-    // traces: per-channel scale, fp16 copy, rsqrt(window energy)
     BPMF_CUDA(cudaMemsetAsync(w.chmax, 0, sizeof(unsigned) * SC, st));
     tc_absmax_kernel<<<dim3(64, (unsigned)SC), 256, 0, st>>>(d_data, sh.N, w.chmax);
     BPMF_LAUNCH_CHECK();
-    tc_data_convert_kernel<<<dim3(128, (unsigned)SC), 256, 0, st>>>(d_data, sh.N, w.dh_pitch, w.chmax, w.dh,
+    tc_data_convert_kernel<<<dim3(128, (unsigned)SC), 256, 0, st>>>(d_data, sh.N, g.dh_pitch, w.chmax, w.dh,
                                                                     w.dh_lo, w.ch_scale);
     BPMF_LAUNCH_CHECK();
-    BPMF_CUDA(cudaMemsetAsync(w.colinv, 0, sizeof(float) * SC * w.ci_pitch, st));
-    int rc = mf_energy(sh, d_data, w.colinv + TC_FRONT, nullptr, w.ci_pitch, true, false, st);
-    if (rc != BPMF_OK) return rc;
+    BPMF_CUDA(cudaMemsetAsync(w.colinv, 0, sizeof(float) * SC * g.ci_pitch, st));
+    return mf_energy(sh, d_data, w.colinv + TC_FRONT, nullptr, g.ci_pitch, true, false, st);
+}
+
+int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int *d_moveouts,
+              const float *d_weights, MfMeta meta, Workspace &trace_ws, bool traces_have_lo, Workspace &tpl_ws,
+              float *d_cc, size_t cc_pitch, cudaStream_t st) {
+    BPMF_REQUIRE(mf_tc_supported(sh.L, sh.step, sh.normalize, sh.network_sum),
+                 "matched filter: shape not supported by the tensor path");
+    BPMF_REQUIRE(!split || traces_have_lo, "matched filter: traces were prepared without the lo part");
+    const TcGeom g = tc_geom(sh, split);
+    TcTraceWs tw = tc_carve_traces(trace_ws, sh, tc_geom(sh, 0), traces_have_lo);
+    TcTplWs w = tc_carve_templates(tpl_ws, sh, g);
+    BPMF_REQUIRE(trace_ws.ok() && tpl_ws.ok(), "matched filter: workspace too small for the tensor path");
+    BPMF_REQUIRE(g.smem_bytes <= TC_SMEM_LIMIT, "matched filter: tensor-path tile exceeds shared memory");
+    const size_t SC = sh.SC();
+
     // templates: resident A images + per-row constants
     tc_template_prep_kernel<<<dim3((unsigned)w.MT, (unsigned)SC), TC_ROWS, 0, st>>>(
-        d_templates, d_moveouts, d_weights, meta.sst, meta.lo, meta.hi, w.ch_scale, (int)sh.T, (int)SC, (int)sh.L,
-        w.n_kc, w.Kc, split, w.a_bytes, w.a_img_bytes, w.aimg, w.row_q, w.row_e, w.row_scale, w.row_ithr,
+        d_templates, d_moveouts, d_weights, meta.sst, meta.lo, meta.hi, tw.ch_scale, (int)sh.T, (int)SC, (int)sh.L,
+        g.n_kc, g.Kc, split, g.a_bytes, g.a_img_bytes, w.aimg, w.row_q, w.row_e, w.row_scale, w.row_ithr,
         w.item_active);
     BPMF_LAUNCH_CHECK();
     // cc_sum is accumulated with reductions: start from zero (also the value of never-computed outputs)
     BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * cc_pitch, st));
 
     TcParams p;
-    p.dh = w.dh; p.dh_lo = w.dh_lo; p.dh_pitch = w.dh_pitch;
-    p.colinv = w.colinv; p.ci_pitch = w.ci_pitch;
+    p.dh = tw.dh; p.dh_lo = tw.dh_lo; p.dh_pitch = g.dh_pitch;
+    p.colinv = tw.colinv; p.ci_pitch = g.ci_pitch;
     p.aimg = w.aimg;
     p.row_q = w.row_q; p.row_e = w.row_e; p.row_scale = w.row_scale; p.row_ithr = w.row_ithr;
     p.item_active = w.item_active;
     p.lo = meta.lo; p.hi = meta.hi;
     p.cc = d_cc; p.cc_pitch = cc_pitch;
-    p.T = (int)sh.T; p.SC = (int)SC; p.MT = w.MT; p.n_kc = w.n_kc; p.Kc = w.Kc; p.split = split ? 1 : 0;
-    p.a_bytes = w.a_bytes; p.a_img_bytes = w.a_img_bytes;
-    p.b_slice_bytes = w.b_slice_bytes; p.b_stage_bytes = w.b_stage_bytes;
-    p.n_tiles = w.n_tiles;
+    p.T = (int)sh.T; p.SC = (int)SC; p.MT = w.MT; p.n_kc = g.n_kc; p.Kc = g.Kc; p.split = split ? 1 : 0;
+    p.a_bytes = g.a_bytes; p.a_img_bytes = g.a_img_bytes;
+    p.b_slice_bytes = g.b_slice_bytes; p.b_stage_bytes = g.b_stage_bytes;
+    p.n_tiles = g.n_tiles;
     p.seg_tiles = TC_SEG_TILES;
-    p.n_seg = (w.n_tiles + TC_SEG_TILES - 1) / TC_SEG_TILES;
+    p.n_seg = (g.n_tiles + TC_SEG_TILES - 1) / TC_SEG_TILES;
     {
         const char *dbg = getenv("BPMF_TC_DEBUG");
         p.debug = dbg ? atoi(dbg) : 0;
     }
     const long long n_items = (long long)p.n_seg * p.MT * p.SC * p.n_kc;
     BPMF_REQUIRE(n_items < (1ll << 31), "matched filter: too many work items for the tensor path");
-    BPMF_CUDA(cudaFuncSetAttribute(mf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bytes));
+    BPMF_CUDA(cudaFuncSetAttribute(mf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     const int grid = (int)std::min<long long>(n_items, (long long)num_sms());
     {
         MainKernelTimer timer(st);
-        mf_tc_kernel<<<grid, TC_THREADS, w.smem_bytes, st>>>(p);
+        mf_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, st>>>(p);
     }
     BPMF_LAUNCH_CHECK();
     return BPMF_OK;

@@ -31,15 +31,21 @@ def mf_cc_pitch(n_corr):
 
 
 class MatchedFilterPlan:
-    """Pre-allocated workspace + output slab for repeated device-resident matched-filter calls."""
+    """Pre-allocated workspaces + output slab for device-resident matched-filter calls.
+
+    The trace-side staging (``prepare``) is separate from the per-template-batch run (``run_batch``) so that
+    many template batches can be run against the same traces -- what BPMF does when it loops template chunks
+    over one day of data (BPMF/similarity_search.py:783-790).  ``run`` does both.
+    """
 
     def __init__(self, n_templates, n_stations, n_components, n_samples_template, n_samples_data,
-                 step=1, normalize="short", network_sum=True, precision="auto", device=None):
+                 step=1, normalize="short", network_sum=True, precision="auto", device=None, batch=None):
         self.lib = _lib.load()
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.T, self.S, self.C = int(n_templates), int(n_stations), int(n_components)
         self.L, self.N, self.step = int(n_samples_template), int(n_samples_data), int(step)
+        self.batch = self.T if batch is None else max(1, min(int(batch), self.T))
         self.normalize = 1 if normalize == "full" else 0
         self.network_sum = 1 if network_sum else 0
         self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
@@ -48,9 +54,13 @@ class MatchedFilterPlan:
             self.L, self.step, self.normalize, self.network_sum, self.precision))
         if self.resolved_precision <= 0:
             raise _lib.BpmfError("precision %r is not available for this shape" % (precision,))
-        ws = int(self.lib.bpmf_mf_workspace_bytes(self.L, self.N, self.T, self.S, self.C, self.step,
-                                                  self.normalize, self.network_sum, self.precision))
-        self.workspace = torch.empty(max(ws, 256), dtype=torch.uint8, device=self.device)
+        self.last_precision = self.resolved_precision
+        tb = int(self.lib.bpmf_mf_trace_workspace_bytes(self.L, self.N, self.S, self.C, self.step, self.normalize,
+                                                        self.network_sum, self.precision))
+        pb = int(self.lib.bpmf_mf_template_workspace_bytes(self.L, self.N, self.batch, self.S, self.C, self.step,
+                                                           self.normalize, self.network_sum, self.precision))
+        self.trace_ws = torch.empty(max(tb, 256), dtype=torch.uint8, device=self.device)
+        self.template_ws = torch.empty(max(pb, 256), dtype=torch.uint8, device=self.device)
         if self.network_sum:
             self.pitch = mf_cc_pitch(self.n_corr)
             self.cc = torch.empty((self.T, self.pitch), dtype=torch.float32, device=self.device)
@@ -59,7 +69,29 @@ class MatchedFilterPlan:
             self.cc = torch.empty((self.T, self.n_corr, self.S, self.C), dtype=torch.float32,
                                   device=self.device)
 
-    def run(self, templates, moveouts, weights, data):
+    def prepare(self, data):
+        """Stage the traces (fp16 copies / window energies) for every later ``run_batch``."""
+        _chk(data, torch.float32, "data")
+        assert tuple(data.shape) == (self.S, self.C, self.N)
+        rc = self.lib.bpmf_mf_prepare_traces_dev(data.data_ptr(), self.step, self.L, self.N, self.S, self.C,
+                                                 self.normalize, self.network_sum, self.precision,
+                                                 self.trace_ws.data_ptr(), self.trace_ws.numel(), _stream_ptr())
+        _lib.check(rc, "mf_prepare_traces_dev")
+
+    def run_batch(self, templates, moveouts, weights, data, t0=0, n=None):
+        """Templates [t0, t0+n) of the (T,...) inputs into rows [t0, t0+n) of the CC slab."""
+        n = min(self.batch, self.T - t0) if n is None else int(n)
+        assert 0 < n <= self.batch and t0 + n <= self.T
+        tp, mv, w = templates[t0:t0 + n], moveouts[t0:t0 + n], weights[t0:t0 + n]
+        rc = self.lib.bpmf_mf_run_dev(
+            tp.data_ptr(), mv.data_ptr(), w.data_ptr(), data.data_ptr(), self.step, self.L, self.N, n, self.S,
+            self.C, self.normalize, self.network_sum, self.precision, self.trace_ws.data_ptr(),
+            self.trace_ws.numel(), self.template_ws.data_ptr(), self.template_ws.numel(),
+            self.cc[t0:t0 + n].data_ptr(), self.pitch, _stream_ptr())
+        _lib.check(rc, "mf_run_dev")
+        self.last_precision = int(self.lib.bpmf_mf_last_precision())
+
+    def run(self, templates, moveouts, weights, data, prepared=False):
         """Enqueue one matched-filter pass; returns the (T, n_corr[, S, C]) CC view on the device."""
         _chk(templates, torch.float32, "templates")
         _chk(moveouts, torch.int32, "moveouts")
@@ -68,13 +100,10 @@ class MatchedFilterPlan:
         assert tuple(templates.shape) == (self.T, self.S, self.C, self.L)
         assert tuple(data.shape) == (self.S, self.C, self.N)
         assert tuple(moveouts.shape) == (self.T, self.S, self.C) == tuple(weights.shape)
-        rc = self.lib.bpmf_matched_filter_dev(
-            templates.data_ptr(), moveouts.data_ptr(), weights.data_ptr(), data.data_ptr(), self.step,
-            self.L, self.N, self.T, self.S, self.C, self.normalize, self.network_sum, self.precision,
-            self.workspace.data_ptr(), self.workspace.numel(), self.cc.data_ptr(), self.pitch,
-            _stream_ptr())
-        _lib.check(rc, "matched_filter_dev")
-        self.last_precision = int(self.lib.bpmf_mf_last_precision())
+        if not prepared:
+            self.prepare(data)
+        for t0 in range(0, self.T, self.batch):
+            self.run_batch(templates, moveouts, weights, data, t0)
         return self.cc[:, : self.n_corr] if self.network_sum else self.cc
 
 
