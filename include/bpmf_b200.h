@@ -49,6 +49,11 @@ const char *bpmf_version(void);
 /* number of kernel launches issued by this library since process start (all threads) */
 unsigned long long bpmf_launch_count(void);
 
+/* The persistent matched-filter kernel occupies every SM (one CTA each, all of its shared memory).
+ * A caller that overlaps a collective (NCCL all-gather of finished CC slabs) with the next batch
+ * reserves a few SMs for it; 0 (default) = use them all. */
+void bpmf_set_reserved_sms(int n);
+
 /* Optional instrumentation for bench.py: while enabled, the dominant kernel of every
  * bpmf_matched_filter_dev / bpmf_beamform_*_dev call made by the calling thread is bracketed by
  * CUDA events on the launching stream (up to 256 launches).  bpmf_main_kernel_times() waits for

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "bpmf_version": (C.c_char_p, []),
     "bpmf_device_count": (C.c_int, []),
     "bpmf_launch_count": (C.c_ulonglong, []),
+    "bpmf_set_reserved_sms": (None, [C.c_int]),
     "bpmf_set_kernel_timing": (None, [C.c_int]),
     "bpmf_main_kernel_times": (C.c_int, [fp, C.c_int]),
     "caract_GPU": (None, []),

@@ -42,6 +42,9 @@ MainKernelTimer::~MainKernelTimer() {
     g_ev_count++;
 }
 
+static std::atomic<int> g_reserved_sms{0};
+int reserved_sms() { return g_reserved_sms.load(); }
+
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;
@@ -153,6 +156,8 @@ extern "C" int bpmf_main_kernel_times(float *ms, int capacity) {
     g_ev_count = 0;
     return n;
 }
+
+extern "C" void bpmf_set_reserved_sms(int n) { g_reserved_sms.store(n < 0 ? 0 : n); }
 
 extern "C" int bpmf_device_count(void) {
     int n = 0;

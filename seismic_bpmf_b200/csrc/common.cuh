@@ -80,6 +80,7 @@ struct DevBuf {
 };
 
 int num_sms();
+int reserved_sms();  // SMs the persistent kernels leave free (bpmf_set_reserved_sms)
 
 // ---------------------------------------------------------------- matched filter internals
 constexpr float MF_GUARD = 1e-6f;  // sum T^2 * sum D^2 <= guard -> exactly 0

@@ -718,7 +718,9 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     const long long n_items = (long long)p.n_seg * p.MT * p.SC * p.n_kc;
     BPMF_REQUIRE(n_items < (1ll << 31), "matched filter: too many work items for the tensor path");
     BPMF_CUDA(cudaFuncSetAttribute(mf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    const int grid = (int)std::min<long long>(n_items, (long long)num_sms());
+    // persistent grid: one CTA per SM, minus the SMs the caller reserved for a concurrent collective
+    const int sms = std::max(1, num_sms() - reserved_sms());
+    const int grid = (int)std::min<long long>(n_items, (long long)sms);
     {
         MainKernelTimer timer(st);
         mf_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, st>>>(p);

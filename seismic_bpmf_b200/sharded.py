@@ -116,3 +116,54 @@ def beamform_max_sharded(features, moveouts, weights_phases, weights_sources, ou
             dev.beam_merge_(best, barg, packed_m[r], packed_a[r])
         return best, barg
     return merge_max_argmax(packed_m, packed_a)
+
+
+class PeerSlabGather:
+    """All-gather of equally sized float32 slabs through NVLink/NVSwitch peer memory, moved by the copy
+    engines instead of SM kernels.
+
+    The matched-filter kernel is persistent and owns every SM (one CTA each, all of its shared memory), so
+    an NCCL kernel enqueued beside it only runs in its tail.  Here every rank PUSHES its finished slab
+    straight into the gather buffers of its peers (torch symmetric memory gives the peer mappings;
+    ``cudaMemcpyAsync`` on a side stream runs on the DMA engines) while the next template batch computes; a
+    device-side barrier per batch tells every rank that the batch is complete everywhere.
+    """
+
+    def __init__(self, n_elements_per_rank, device, group=None, n_buffers=2):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = int(n_elements_per_rank)
+        self.stream = torch.cuda.Stream(device=device)
+        self.local, self.peers, self.handles = [], [], []
+        for _ in range(n_buffers):
+            buf = symm_mem.empty(self.world * self.n, dtype=torch.float32, device=device)
+            handle = symm_mem.rendezvous(buf, group.group_name)
+            self.local.append(buf)
+            self.handles.append(handle)
+            self.peers.append([handle.get_buffer(r, (self.world * self.n,), torch.float32)
+                               for r in range(self.world)])
+        self._event = torch.cuda.Event()
+
+    def push(self, b, slab_flat):
+        """Copy this rank's slab (flat, <= n elements, produced on the current stream) into slot ``rank`` of
+        buffer ``b`` on every rank; returns immediately (work runs on the side stream)."""
+        n = slab_flat.numel()
+        assert n <= self.n and slab_flat.is_contiguous()
+        self._event.record()
+        self.stream.wait_event(self._event)
+        with torch.cuda.stream(self.stream):
+            lo = self.rank * self.n
+            for k in range(self.world):
+                r = (self.rank + k) % self.world  # own copy first, then the ring of peers
+                self.peers[b][r][lo: lo + n].copy_(slab_flat, non_blocking=True)
+            self.handles[b].barrier(channel=0)  # every rank's push of this batch has landed everywhere
+
+    def gathered(self, b, rows, pitch):
+        """View of buffer ``b`` as (world, rows, pitch) once the side stream has been waited for."""
+        return self.local[b][: self.world * self.n].view(self.world, -1)[:, : rows * pitch].view(self.world, rows, pitch)
+
+    def wait(self):
+        """Make the current stream wait for every push/barrier enqueued so far."""
+        torch.cuda.current_stream().wait_stream(self.stream)
