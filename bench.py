@@ -233,7 +233,7 @@ def run_ours(args, rank, world, local_rank):
         planted = {}
     # N > 1: the per-rank pass runs in template batches so that the all-gather of one batch's CC slab
     # overlaps the kernels of the next one
-    batch = T if world == 1 else 128
+    batch = T if world == 1 else (128 if world <= 2 else 64)
     plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, precision=args.precision, device=device, batch=batch)
     n_corr = plan.n_corr
     units = T * S * Cc * n_corr  # per rank, per step
@@ -244,13 +244,13 @@ def run_ours(args, rank, world, local_rank):
 
         try:  # copy-engine pushes over NVLink peer memory: overlap with the persistent kernel without taking SMs
             gather = sharded.PeerSlabGather(batch * plan.pitch, device)
-            collective = ("all-gather of per-shard CC slabs, one per 128-template batch, pushed to peer memory over "
+            collective = ("all-gather of per-shard CC slabs, one per %d-template batch, pushed to peer memory over " % batch +
                           "NVLink by the copy engines (torch symmetric memory) while the next batch computes")
         except Exception as exc:  # noqa: BLE001 -- fall back to NCCL kernels
             if rank == 0:
                 print("bench: symmetric memory unavailable (%s); using NCCL all-gather" % exc, file=sys.stderr)
             gbufs = [torch.empty(world * batch * plan.pitch, dtype=torch.float32, device=device) for _ in range(2)]
-            collective = "NCCL all-gather of per-shard CC slabs, one per 128-template batch"
+            collective = "NCCL all-gather of per-shard CC slabs, one per %d-template batch" % batch
 
     def step_fn():
         if world == 1:

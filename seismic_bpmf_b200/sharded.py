@@ -129,13 +129,16 @@ class PeerSlabGather:
     device-side barrier per batch tells every rank that the batch is complete everywhere.
     """
 
-    def __init__(self, n_elements_per_rank, device, group=None, n_buffers=2):
+    def __init__(self, n_elements_per_rank, device, group=None, n_buffers=2, n_streams=3):
         import torch.distributed._symmetric_memory as symm_mem
 
         group = dist.group.WORLD if group is None else group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.n = int(n_elements_per_rank)
-        self.stream = torch.cuda.Stream(device=device)
+        self.stream = torch.cuda.Stream(device=device)  # ordering stream: barriers + the wait() handle
+        # copies to different peers go out on several streams so that more than one copy engine is busy
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, min(n_streams, self.world - 1)))]
+        self._copy_events = [torch.cuda.Event() for _ in self.copy_streams]
         self.local, self.peers, self.handles = [], [], []
         for _ in range(n_buffers):
             buf = symm_mem.empty(self.world * self.n, dtype=torch.float32, device=device)
@@ -152,12 +155,18 @@ class PeerSlabGather:
         n = slab_flat.numel()
         assert n <= self.n and slab_flat.is_contiguous()
         self._event.record()
-        self.stream.wait_event(self._event)
+        lo = self.rank * self.n
+        for i, cs in enumerate(self.copy_streams):
+            cs.wait_event(self._event)
+            cs.wait_stream(self.stream)  # keep batches ordered behind the previous barrier
+            with torch.cuda.stream(cs):
+                for k in range(i, self.world, len(self.copy_streams)):
+                    r = (self.rank + k) % self.world  # own copy first, then the ring of peers
+                    self.peers[b][r][lo: lo + n].copy_(slab_flat, non_blocking=True)
+                self._copy_events[i].record()
         with torch.cuda.stream(self.stream):
-            lo = self.rank * self.n
-            for k in range(self.world):
-                r = (self.rank + k) % self.world  # own copy first, then the ring of peers
-                self.peers[b][r][lo: lo + n].copy_(slab_flat, non_blocking=True)
+            for ev in self._copy_events:
+                self.stream.wait_event(ev)
             self.handles[b].barrier(channel=0)  # every rank's push of this batch has landed everywhere
 
     def gathered(self, b, rows, pitch):
