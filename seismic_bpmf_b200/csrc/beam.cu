@@ -7,8 +7,10 @@
 //   prestack : U[s,p,t] = sum_c weights_phases[s,c,p] * features[s,c,t]        (HBM-bound)
 //   beam     : b[k,t]   = sum_{s,p} weights_sources[k,s] * U[s,p,t + tau[k,s,p]]
 //              CTA = 2048-sample time tile x a chunk of sources, processed 8 sources at a time
-//              with 8x8 register accumulators per thread.  The (station, phase) loop is OUTER so
-//              only one row segment of U lives in shared memory at a time; every gather-FMA costs
+//              with 8x8 register accumulators per thread.  The (station, phase) loop is OUTER: one
+//              row segment of U per (station, phase) -- one window covers the block's 8 sources when
+//              their moveouts are close, as for neighbouring grid points -- streams through a
+//              cp.async double buffer while the previous row is consumed; every gather-FMA costs
 //              one conflict-free 4-byte LDS (lanes = consecutive samples).  Roofline: shared-memory
 //              bandwidth, 128 B/clk/SM = 32 gather-FMA/clk/SM.
 //   reduce   : "max" keeps a running (max, argmax) per sample in registers and merges source
@@ -24,23 +26,25 @@ constexpr int B_TT = B_THREADS * B_R;     // 2048-sample tile
 constexpr int B_KB = 8;                   // sources per register block
 constexpr int B_CAP = B_TT + 1024;        // staged row segment (floats)
 
+// U rows have a pitch that is a multiple of 4 floats (16-byte aligned rows for the float4 staging of the
+// beam kernel); the pad beyond N is zero.
 __global__ void beam_prestack_kernel(const float *__restrict__ features,
-                                     const float *__restrict__ wp, int C, int P, size_t N,
+                                     const float *__restrict__ wp, int C, int P, size_t N, size_t pitch,
                                      float *__restrict__ U) {
     const int sp = blockIdx.y;  // s * P + p
     const int s = sp / P, p = sp % P;
     const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (t >= N) return;
+    if (t >= pitch) return;
     float a[4] = {0.f, 0.f, 0.f, 0.f};
-    const int n_here = (N - t >= 4) ? 4 : (int)(N - t);
+    const int n_here = (t >= N) ? 0 : ((N - t >= 4) ? 4 : (int)(N - t));
     for (int c = 0; c < C; c++) {
         const float w = wp[((size_t)s * C + c) * P + p];
         if (w == 0.f) continue;
         const float *f = features + ((size_t)s * C + c) * N + t;
         for (int i = 0; i < n_here; i++) a[i] = fmaf(w, f[i], a[i]);
     }
-    float *u = U + (size_t)sp * N + t;
-    for (int i = 0; i < n_here; i++) u[i] = a[i];
+    float *u = U + (size_t)sp * pitch + t;
+    for (int i = 0; i < 4 && t + i < pitch; i++) u[i] = a[i];
 }
 
 __device__ __forceinline__ unsigned ordered_bits(float f) {
@@ -78,16 +82,40 @@ __global__ void beam_source_bounds_kernel(const int *__restrict__ tau, const flo
     thi[k] = (int)(hi < -1 ? -1 : hi);
 }
 
+// 16-byte async copy global -> shared with zero fill when `valid` is false (LDGSTS.128)
+__device__ __forceinline__ void cp_async_f32x4(float *smem_dst, const float *gmem_src, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int src_bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// stage samples [first, first + B_CAP) of one U row into `buf`, zero outside the row; `first` and the row
+// pitch are multiples of 4, so every 16-byte piece is entirely inside or entirely outside [0, pitch)
+__device__ __forceinline__ void beam_stage_async(float *buf, const float *row, long long first, long long pitch,
+                                                 int tid) {
+#pragma unroll
+    for (int i = tid * 4; i < B_CAP; i += B_THREADS * 4) {
+        const long long g = first + i;
+        const bool ok = g >= 0 && g < pitch;
+        cp_async_f32x4(buf + i, row + (ok ? g : 0), ok);
+    }
+}
+
 template <bool REDUCE_MAX>
 __global__ void __launch_bounds__(B_THREADS, 2)
     beam_kernel(const float *__restrict__ U, const int *__restrict__ tau,
                 const float *__restrict__ beta, const int *__restrict__ tlo,
-                const int *__restrict__ thi, size_t K, int S, int P, long long N, int strict,
+                const int *__restrict__ thi, size_t K, int S, int P, long long N, long long pitch, int strict,
                 size_t k_chunk, unsigned long long *__restrict__ keys, float *__restrict__ beam) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *buf = reinterpret_cast<float *>(smem_raw);            // B_CAP
-    int *tau_s = reinterpret_cast<int *>(buf + B_CAP);           // B_KB * S * P
-    float *beta_s = reinterpret_cast<float *>(tau_s + B_KB * S * P);  // B_KB * S
+    float *buf0 = reinterpret_cast<float *>(smem_raw);                 // 2 x B_CAP (double buffer)
+    int *tau_s = reinterpret_cast<int *>(buf0 + 2 * B_CAP);            // B_KB * S * P
+    float *beta_s = reinterpret_cast<float *>(tau_s + B_KB * S * P);   // B_KB * S
+    int *wlo_s = reinterpret_cast<int *>(beta_s + B_KB * S);           // S * P: window start per (station, phase)
+    int *wide_s = wlo_s + S * P;                                       // S * P: 1 = moveouts do not fit one window
 
     const int tid = threadIdx.x;
     const long long t0 = (long long)blockIdx.x * B_TT;
@@ -112,6 +140,25 @@ __global__ void __launch_bounds__(B_THREADS, 2)
             beta_s[i] = (kk < nk) ? beta[(kb + kk) * S + (i - kk * S)] : 0.f;
         }
         __syncthreads();
+        // one staged window per (station, phase) covers every source of the block when their moveouts
+        // are close (neighbouring grid points); otherwise the slow path restages per source
+        for (int sp = tid; sp < SP; sp += B_THREADS) {
+            const int s = sp / P;
+            int mn = 0x7fffffff, mx = -0x7fffffff;
+            for (int kk = 0; kk < B_KB; kk++) {
+                if (beta_s[kk * S + s] == 0.f) continue;
+                const int v = tau_s[kk * SP + sp];
+                mn = v < mn ? v : mn;
+                mx = v > mx ? v : mx;
+            }
+            if (mx < mn) { mn = 0; mx = 0; wide_s[sp] = 2; }  // no source uses this row
+            else {
+                mn = (mn >= 0) ? (mn & ~3) : -((-mn + 3) & ~3);  // align down: 16-byte staging
+                wide_s[sp] = ((long long)mx - mn + B_TT > B_CAP) ? 1 : 0;
+            }
+            wlo_s[sp] = mn;
+        }
+        __syncthreads();
 
         float acc[B_KB][B_R];
 #pragma unroll
@@ -119,31 +166,55 @@ __global__ void __launch_bounds__(B_THREADS, 2)
 #pragma unroll
             for (int r = 0; r < B_R; r++) acc[kk][r] = 0.f;
 
+        // software pipeline over (station, phase): row sp+1 streams in with cp.async while row sp is used
+        if (wide_s[0] != 2) beam_stage_async(buf0, U, t0 + wlo_s[0], pitch, tid);
+        cp_async_commit();
         for (int sp = 0; sp < SP; sp++) {
             const int s = sp / P;
-            const float *row = U + (size_t)sp * N;
-            long long wlo = 0;
-            bool staged = false;
+            float *buf = buf0 + (sp & 1) * B_CAP;
+            if (sp + 1 < SP && wide_s[sp + 1] != 2)
+                beam_stage_async(buf0 + ((sp + 1) & 1) * B_CAP, U + (size_t)(sp + 1) * pitch, t0 + wlo_s[sp + 1], pitch,
+                                 tid);
+            cp_async_commit();
+            cp_async_wait<1>();  // row sp has landed (row sp+1 may still be in flight)
+            __syncthreads();
+            const int wide = wide_s[sp];
+            if (wide == 0) {
+                const int wlo = wlo_s[sp];
 #pragma unroll
-            for (int kk = 0; kk < B_KB; kk++) {
-                const float b = beta_s[kk * S + s];
-                if (b == 0.f) continue;  // CTA-uniform
-                const long long tk = tau_s[kk * SP + sp];
-                if (!staged || tk < wlo || tk + B_TT > wlo + B_CAP) {
-                    __syncthreads();
-                    wlo = tk - (B_CAP - B_TT) / 4;  // keep most of the slack ahead of this source
-                    for (int i = tid; i < B_CAP; i += B_THREADS) {
-                        const long long g = t0 + wlo + i;
-                        buf[i] = (g >= 0 && g < N) ? __ldg(row + g) : 0.f;
-                    }
-                    staged = true;
-                    __syncthreads();
+                for (int kk = 0; kk < B_KB; kk++) {
+                    const float b = beta_s[kk * S + s];
+                    if (b == 0.f) continue;  // CTA-uniform
+                    const float *src = buf + (tau_s[kk * SP + sp] - wlo) + tid;
+#pragma unroll
+                    for (int r = 0; r < B_R; r++) acc[kk][r] = fmaf(b, src[B_THREADS * r], acc[kk][r]);
                 }
-                const float *src = buf + (int)(tk - wlo) + tid;
+            } else if (wide == 1) {
+                // moveouts of this block spread beyond one window: restage per source (synchronous)
+                const float *row = U + (size_t)sp * pitch;
+                long long wlo = wlo_s[sp];
 #pragma unroll
-                for (int r = 0; r < B_R; r++) acc[kk][r] = fmaf(b, src[B_THREADS * r], acc[kk][r]);
+                for (int kk = 0; kk < B_KB; kk++) {
+                    const float b = beta_s[kk * S + s];
+                    if (b == 0.f) continue;
+                    const long long tk = tau_s[kk * SP + sp];
+                    if (tk < wlo || tk + B_TT > wlo + B_CAP) {
+                        __syncthreads();
+                        wlo = tk;
+                        for (int i = tid; i < B_CAP; i += B_THREADS) {
+                            const long long g = t0 + wlo + i;
+                            buf[i] = (g >= 0 && g < N) ? __ldg(row + g) : 0.f;
+                        }
+                        __syncthreads();
+                    }
+                    const float *src = buf + (int)(tk - wlo) + tid;
+#pragma unroll
+                    for (int r = 0; r < B_R; r++) acc[kk][r] = fmaf(b, src[B_THREADS * r], acc[kk][r]);
+                }
             }
+            __syncthreads();  // everyone is done with buf before it is refilled two rows later
         }
+        cp_async_wait<0>();
 
 #pragma unroll
         for (int kk = 0; kk < B_KB; kk++) {
@@ -202,7 +273,7 @@ __global__ void beam_merge_kernel(float *__restrict__ ma, int *__restrict__ aa,
 }
 
 static size_t beam_smem_bytes(size_t S, size_t P) {
-    return sizeof(float) * B_CAP + sizeof(int) * B_KB * S * P + sizeof(float) * B_KB * S;
+    return sizeof(float) * 2 * B_CAP + sizeof(int) * B_KB * S * P + sizeof(float) * B_KB * S + 2 * sizeof(int) * S * P;
 }
 
 struct BeamWs {
@@ -213,7 +284,7 @@ struct BeamWs {
 
 static BeamWs carve(Workspace &ws, size_t K, size_t S, size_t P, size_t N) {
     BeamWs b;
-    b.U = ws.take<float>(S * P * N);
+    b.U = ws.take<float>(S * P * align_up(N, 4));
     b.tlo = ws.take<int>(K);
     b.thi = ws.take<int>(K);
     b.keys = ws.take<unsigned long long>(N);
@@ -230,11 +301,12 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
     BeamWs b = carve(ws, K, S, P, N);
     BPMF_REQUIRE(ws.ok(), "beamform: workspace too small (%zu < %zu)", ws_bytes, ws.used);
     const size_t smem = beam_smem_bytes(S, P);
+    const size_t pitch = align_up(N, 4);
     BPMF_REQUIRE(smem <= 200 * 1024, "beamform: too many stations x phases for one tile (%zu x %zu)", S, P);
 
     {
-        dim3 grid((unsigned)((N + 1023) / 1024), (unsigned)(S * P));
-        beam_prestack_kernel<<<grid, 256, 0, st>>>(d_features, d_wp, (int)C, (int)P, N, b.U);
+        dim3 grid((unsigned)((pitch + 1023) / 1024), (unsigned)(S * P));
+        beam_prestack_kernel<<<grid, 256, 0, st>>>(d_features, d_wp, (int)C, (int)P, N, pitch, b.U);
         BPMF_LAUNCH_CHECK();
     }
     if (K > 0) {
@@ -257,7 +329,7 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
             beam_kernel<true><<<grid, B_THREADS, smem, st>>>(b.U, d_tau, d_beta, b.tlo, b.thi, K,
-                                                             (int)S, (int)P, (long long)N,
+                                                             (int)S, (int)P, (long long)N, (long long)pitch,
                                                              flexible ? 0 : 1, k_chunk, b.keys, nullptr);
             BPMF_LAUNCH_CHECK();
         }
@@ -276,7 +348,7 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
         MainKernelTimer timer(st);
         dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
         beam_kernel<false><<<grid, B_THREADS, smem, st>>>(b.U, d_tau, d_beta, b.tlo, b.thi, K, (int)S,
-                                                          (int)P, (long long)N, flexible ? 0 : 1,
+                                                          (int)P, (long long)N, (long long)pitch, flexible ? 0 : 1,
                                                           k_chunk, nullptr, d_beam);
         BPMF_LAUNCH_CHECK();
     }
