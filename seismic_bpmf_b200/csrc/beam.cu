@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(B_THREADS, 2)
     float *beta_s = reinterpret_cast<float *>(tau_s + B_KB * S * P);   // B_KB * S
     int *wlo_s = reinterpret_cast<int *>(beta_s + B_KB * S);           // S * P: window start per (station, phase)
     int *wide_s = wlo_s + S * P;                                       // S * P: 1 = moveouts do not fit one window
+    // S * P * B_KB packed (offset in window, weight bits), 16-byte aligned for the broadcast LDS.128
+    int2 *pk_s = reinterpret_cast<int2 *>((reinterpret_cast<uintptr_t>(wide_s + S * P) + 15) & ~(uintptr_t)15);
 
     const int tid = threadIdx.x;
     const long long t0 = (long long)blockIdx.x * B_TT;
@@ -157,6 +159,8 @@ __global__ void __launch_bounds__(B_THREADS, 2)
                 wide_s[sp] = ((long long)mx - mn + B_TT > B_CAP) ? 1 : 0;
             }
             wlo_s[sp] = mn;
+            for (int kk = 0; kk < B_KB; kk++)
+                pk_s[sp * B_KB + kk] = make_int2(tau_s[kk * SP + sp] - mn, __float_as_int(beta_s[kk * S + s]));
         }
         __syncthreads();
 
@@ -180,14 +184,25 @@ __global__ void __launch_bounds__(B_THREADS, 2)
             __syncthreads();
             const int wide = wide_s[sp];
             if (wide == 0) {
-                const int wlo = wlo_s[sp];
+                // straight-line code over the block's 8 sources: (offset, weight) pairs come as broadcast
+                // LDS.128, zero-weight (source, station) pairs are predicated off instead of branched over
+                int2 pk[B_KB];
+                const int4 *pk4 = reinterpret_cast<const int4 *>(pk_s + sp * B_KB);
+#pragma unroll
+                for (int q = 0; q < B_KB / 2; q++) {
+                    const int4 v = pk4[q];
+                    pk[2 * q] = make_int2(v.x, v.y);
+                    pk[2 * q + 1] = make_int2(v.z, v.w);
+                }
 #pragma unroll
                 for (int kk = 0; kk < B_KB; kk++) {
-                    const float b = beta_s[kk * S + s];
-                    if (b == 0.f) continue;  // CTA-uniform
-                    const float *src = buf + (tau_s[kk * SP + sp] - wlo) + tid;
+                    const float b = __int_as_float(pk[kk].y);
+                    const float *src = buf + pk[kk].x + tid;
 #pragma unroll
-                    for (int r = 0; r < B_R; r++) acc[kk][r] = fmaf(b, src[B_THREADS * r], acc[kk][r]);
+                    for (int r = 0; r < B_R; r++) {
+                        const float u = src[B_THREADS * r];
+                        acc[kk][r] = (b != 0.f) ? fmaf(b, u, acc[kk][r]) : acc[kk][r];
+                    }
                 }
             } else if (wide == 1) {
                 // moveouts of this block spread beyond one window: restage per source (synchronous)
@@ -273,7 +288,8 @@ __global__ void beam_merge_kernel(float *__restrict__ ma, int *__restrict__ aa,
 }
 
 static size_t beam_smem_bytes(size_t S, size_t P) {
-    return sizeof(float) * 2 * B_CAP + sizeof(int) * B_KB * S * P + sizeof(float) * B_KB * S + 2 * sizeof(int) * S * P;
+    return sizeof(float) * 2 * B_CAP + sizeof(int) * B_KB * S * P + sizeof(float) * B_KB * S +
+           2 * sizeof(int) * (S * P + 1) + sizeof(int2) * B_KB * S * P + 16;
 }
 
 struct BeamWs {
