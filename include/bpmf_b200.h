@@ -214,6 +214,20 @@ int bpmf_time_dependent_threshold_dev(float *d_series, size_t pitch, size_t n_se
                                       size_t shift_samp, void *d_workspace, size_t workspace_bytes,
                                       float *d_threshold, size_t threshold_pitch, void *stream);
 
+/* Candidate detections without moving the CC slab off the GPU (replaces the
+ * per-template download + time_dependent_threshold + peak selection of
+ * BPMF/similarity_search.py:600-666).  For each of the n_series rows: rms threshold as above (the rows
+ * are NOT modified), then every sample with cc > threshold (mode 0) that also survives the
+ * declustering of select_cc_indexes with `search_win` (mode 1; libc.c:441-485) is appended, unordered,
+ * to the compact lists (series, index, cc, threshold).  *d_count receives the number of hits, which
+ * may exceed `capacity` (then only `capacity` records were written).  Workspace:
+ * bpmf_threshold_workspace_bytes(). */
+int bpmf_detect_dev(const float *d_series, size_t pitch, size_t n_series, const float *d_gaussian_sample,
+                    float num_dev, size_t num_samples, size_t half_window_samp, size_t shift_samp,
+                    size_t search_win, int mode, void *d_workspace, size_t workspace_bytes,
+                    unsigned *d_count, int *d_series_idx, int *d_index, float *d_value, float *d_thr_value,
+                    size_t capacity, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,16 +79,26 @@ __global__ void thr_fill_kernel(float *__restrict__ x, size_t pitch, size_t n,
     if (xs[i] == 0.f) xs[i] = __fadd_rn(stat[b].center, __fmul_rn(gauss[i % GAUSS_LEN], stat[b].dev));
 }
 
-// one CTA per (window, series): mean then rms deviation of W samples (libc.c:615-627)
+// sample i of a series as libc.c:606-612 leaves it: zeros replaced by center + gaussian[i % 500] * dev
+__device__ __forceinline__ float thr_sample(const float *xs, size_t i, const float *gauss, float center, float dev) {
+    const float v = xs[i];
+    return (v == 0.f) ? __fadd_rn(center, __fmul_rn(gauss[i % GAUSS_LEN], dev)) : v;
+}
+
+// one CTA per (window, series): mean then rms deviation of W samples (libc.c:615-627); zeros are
+// substituted on the fly, so the series itself need not have been filled
 __global__ void thr_window_kernel(const float *__restrict__ x, size_t pitch, size_t W, size_t shift,
-                                  size_t n_win, float num_dev, float *__restrict__ tw) {
+                                  size_t n_win, float num_dev, const float *__restrict__ gauss,
+                                  const ThrStat *__restrict__ stat, float *__restrict__ tw) {
     __shared__ double red[32];
     __shared__ float mean_s;
     const size_t b = blockIdx.y, w = blockIdx.x;
-    const float *xs = x + b * pitch + w * shift;
+    const float *xs = x + b * pitch;
+    const size_t o = w * shift;
+    const float center = stat[b].center, sdev = stat[b].dev;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double acc = 0.0;
-    for (size_t i = threadIdx.x; i < W; i += blockDim.x) acc += (double)xs[i];
+    for (size_t i = threadIdx.x; i < W; i += blockDim.x) acc += (double)thr_sample(xs, o + i, gauss, center, sdev);
     acc = warp_sum(acc);
     if (lane == 0) red[wid] = acc;
     __syncthreads();
@@ -101,7 +111,7 @@ __global__ void thr_window_kernel(const float *__restrict__ x, size_t pitch, siz
     const float mean = mean_s;
     acc = 0.0;
     for (size_t i = threadIdx.x; i < W; i += blockDim.x) {
-        const double d = (double)__fsub_rn(xs[i], mean);
+        const double d = (double)__fsub_rn(thr_sample(xs, o + i, gauss, center, sdev), mean);
         acc += d * d;
     }
     acc = warp_sum(acc);
@@ -124,12 +134,8 @@ __device__ __forceinline__ float thr_tw1(const float *tw, long long w) {
     return (d0 < 0.f) ? __fsub_rn(tw[w], d0) : tw[w];
 }
 
-__global__ void thr_expand_kernel(const float *__restrict__ tw, size_t n_win, size_t n, size_t shift,
-                                  float *__restrict__ thr, size_t thr_pitch) {
-    const size_t b = blockIdx.y;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *t = tw + b * n_win;
+// threshold at sample i from the raw window values t[0..n_win)
+__device__ __forceinline__ float thr_at(const float *t, size_t n_win, size_t n, size_t shift, size_t i) {
     long long w;
     if (i < shift) w = 0;
     else if (i >= n - shift) w = (long long)n_win - 1;
@@ -142,7 +148,51 @@ __global__ void thr_expand_kernel(const float *__restrict__ tw, size_t n_win, si
         const float d1 = __fsub_rn(thr_tw1(t, w + 1), v);
         if (d1 > 0.f) v = __fadd_rn(v, d1);
     }
-    thr[b * thr_pitch + i] = v;
+    return v;
+}
+
+__global__ void thr_expand_kernel(const float *__restrict__ tw, size_t n_win, size_t n, size_t shift,
+                                  float *__restrict__ thr, size_t thr_pitch) {
+    const size_t b = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    thr[b * thr_pitch + i] = thr_at(tw + b * n_win, n_win, n, shift, i);
+}
+
+// Candidate detections straight from the CC slab: sample i of series b is reported when
+// cc > threshold(i) and, in mode 1, it also survives the declustering of select_cc_indexes
+// (libc.c:441-485, closed form below).  Survivors are appended to a compact list; only that list has to
+// leave the GPU.
+__global__ void detect_kernel(const float *__restrict__ x, size_t pitch, const float *__restrict__ tw, size_t n_win,
+                              size_t n, size_t shift, long long search_win, int mode, unsigned *__restrict__ count,
+                              int *__restrict__ o_series, int *__restrict__ o_index, float *__restrict__ o_value,
+                              float *__restrict__ o_thr, unsigned capacity) {
+    const size_t b = blockIdx.y;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (long long)n) return;
+    const float *cc = x + b * pitch;
+    const float v = cc[j];
+    const float th = thr_at(tw + b * n_win, n_win, n, shift, (size_t)j);
+    bool keep = v > th;
+    if (keep && mode == 1) {
+        const long long a = (j <= search_win) ? 0 : j - search_win;
+        for (long long q = a; q < j; q++)
+            if (cc[q] > v) { keep = false; break; }
+        if (keep) {
+            const long long e = (j + search_win < (long long)n - 1) ? j + search_win : (long long)n - 1;
+            for (long long i = j + 1; i <= e; i++)
+                if (!(cc[i] < v)) { keep = false; break; }
+        }
+    }
+    if (keep) {
+        const unsigned slot = atomicAdd(count, 1u);
+        if (slot < capacity) {
+            o_series[slot] = (int)b;
+            o_index[slot] = (int)j;
+            o_value[slot] = v;
+            o_thr[slot] = th;
+        }
+    }
 }
 
 static bool thr_geometry(size_t n, size_t half, size_t shift, size_t *W, size_t *n_win) {
@@ -165,21 +215,12 @@ extern "C" size_t bpmf_threshold_workspace_bytes(size_t n_series, size_t n, size
     return ws.used;
 }
 
-extern "C" int bpmf_time_dependent_threshold_dev(float *d_series, size_t pitch, size_t B,
-                                                 const float *d_gauss, float num_dev, size_t n,
-                                                 size_t half, size_t shift, void *d_workspace,
-                                                 size_t workspace_bytes, float *d_thr,
-                                                 size_t thr_pitch, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (B == 0) return BPMF_OK;
-    size_t W, n_win;
-    BPMF_REQUIRE(thr_geometry(n, half, shift, &W, &n_win),
-                 "time_dependent_threshold: invalid geometry n=%zu half_window=%zu shift=%zu", n, half, shift);
+// global statistics + per-window mean/std -> raw window thresholds tw[B][n_win]; fills the series in place
+// only when `fill` is set (the libc ABI mutates its input, libc.c:606-612)
+static int thr_windows(float *d_series, size_t pitch, size_t B, const float *d_gauss, float num_dev, size_t n,
+                       size_t W, size_t shift, size_t n_win, bool fill, ThrStat *stat, float *tw, cudaStream_t st) {
     BPMF_REQUIRE(B <= 65535, "time_dependent_threshold: more than 65535 series per call");
-    Workspace ws(d_workspace, workspace_bytes);
-    ThrStat *stat = ws.take<ThrStat>(B);
-    float *tw = ws.take<float>(B * n_win);
-    BPMF_REQUIRE(ws.ok(), "time_dependent_threshold: workspace too small");
+    BPMF_REQUIRE(n_win < ((size_t)1 << 31), "time_dependent_threshold: too many windows");
     BPMF_CUDA(cudaMemsetAsync(stat, 0, sizeof(ThrStat) * B, st));
     const size_t n_head = (n / W) * W;  // libc.c:553: only whole windows enter the global stats
     const unsigned gx = (unsigned)std::min<size_t>((n_head + 255) / 256, 1024);
@@ -192,13 +233,61 @@ extern "C" int bpmf_time_dependent_threshold_dev(float *d_series, size_t pitch, 
     BPMF_LAUNCH_CHECK();
     thr_finish_stat_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(stat, B, 1);
     BPMF_LAUNCH_CHECK();
-    thr_fill_kernel<<<dim3(nb, (unsigned)B), 256, 0, st>>>(d_series, pitch, n, d_gauss, stat);
+    thr_window_kernel<<<dim3((unsigned)n_win, (unsigned)B), 256, 0, st>>>(d_series, pitch, W, shift, n_win, num_dev,
+                                                                         d_gauss, stat, tw);
     BPMF_LAUNCH_CHECK();
-    BPMF_REQUIRE(n_win < ((size_t)1 << 31), "time_dependent_threshold: too many windows");
-    thr_window_kernel<<<dim3((unsigned)n_win, (unsigned)B), 256, 0, st>>>(d_series, pitch, W, shift,
-                                                                         n_win, num_dev, tw);
+    if (fill) {
+        thr_fill_kernel<<<dim3(nb, (unsigned)B), 256, 0, st>>>(d_series, pitch, n, d_gauss, stat);
+        BPMF_LAUNCH_CHECK();
+    }
+    return BPMF_OK;
+}
+
+extern "C" int bpmf_time_dependent_threshold_dev(float *d_series, size_t pitch, size_t B,
+                                                 const float *d_gauss, float num_dev, size_t n,
+                                                 size_t half, size_t shift, void *d_workspace,
+                                                 size_t workspace_bytes, float *d_thr,
+                                                 size_t thr_pitch, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) return BPMF_OK;
+    size_t W, n_win;
+    BPMF_REQUIRE(thr_geometry(n, half, shift, &W, &n_win),
+                 "time_dependent_threshold: invalid geometry n=%zu half_window=%zu shift=%zu", n, half, shift);
+    Workspace ws(d_workspace, workspace_bytes);
+    ThrStat *stat = ws.take<ThrStat>(B);
+    float *tw = ws.take<float>(B * n_win);
+    BPMF_REQUIRE(ws.ok(), "time_dependent_threshold: workspace too small");
+    int rc = thr_windows(d_series, pitch, B, d_gauss, num_dev, n, W, shift, n_win, true, stat, tw, st);
+    if (rc != BPMF_OK) return rc;
+    thr_expand_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)B), 256, 0, st>>>(tw, n_win, n, shift, d_thr,
+                                                                                      thr_pitch);
     BPMF_LAUNCH_CHECK();
-    thr_expand_kernel<<<dim3(nb, (unsigned)B), 256, 0, st>>>(tw, n_win, n, shift, d_thr, thr_pitch);
+    return BPMF_OK;
+}
+
+extern "C" int bpmf_detect_dev(const float *d_series, size_t pitch, size_t B, const float *d_gauss, float num_dev,
+                               size_t n, size_t half, size_t shift, size_t search_win, int mode, void *d_workspace,
+                               size_t workspace_bytes, unsigned *d_count, int *d_series_idx, int *d_index,
+                               float *d_value, float *d_thr_value, size_t capacity, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    BPMF_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned), st));
+    if (B == 0) return BPMF_OK;
+    size_t W, n_win;
+    BPMF_REQUIRE(thr_geometry(n, half, shift, &W, &n_win),
+                 "detect: invalid geometry n=%zu half_window=%zu shift=%zu", n, half, shift);
+    BPMF_REQUIRE(mode == 0 || mode == 1, "detect: mode must be 0 (above threshold) or 1 (select_cc_indexes)");
+    BPMF_REQUIRE(capacity < ((size_t)1 << 32), "detect: capacity too large");
+    Workspace ws(d_workspace, workspace_bytes);
+    ThrStat *stat = ws.take<ThrStat>(B);
+    float *tw = ws.take<float>(B * n_win);
+    BPMF_REQUIRE(ws.ok(), "detect: workspace too small");
+    // the series is NOT modified: zeros are substituted on the fly inside the window statistics
+    int rc = thr_windows(const_cast<float *>(d_series), pitch, B, d_gauss, num_dev, n, W, shift, n_win, false, stat,
+                         tw, st);
+    if (rc != BPMF_OK) return rc;
+    detect_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)B), 256, 0, st>>>(
+        d_series, pitch, tw, n_win, n, shift, (long long)search_win, mode, d_count, d_series_idx, d_index, d_value,
+        d_thr_value, (unsigned)capacity);
     BPMF_LAUNCH_CHECK();
     return BPMF_OK;
 }

@@ -191,3 +191,42 @@ def time_dependent_threshold_dev(series, gaussian_sample, num_dev, half_window_s
                                                n, _stream_ptr())
     _lib.check(rc, "time_dependent_threshold_dev")
     return thr
+
+
+def detect_dev(series, gaussian_sample, num_dev, half_window_samp, shift_samp, search_win=0, mode="above",
+               n_valid=None, capacity=1 << 20):
+    """Candidate detections from a (B, pitch) device slab of CC series without downloading it.
+
+    mode="above": every sample with cc > rms threshold (what BPMF/similarity_search.py:232-233 starts from);
+    mode="select": additionally the declustering of ``clib.select_cc_indexes`` with ``search_win``.
+    Returns numpy arrays (series, index, cc, threshold) sorted by (series, index).  Raises if more than
+    ``capacity`` candidates were found.
+    """
+    import numpy as np
+
+    lib = _lib.load()
+    assert series.is_cuda and series.dtype == torch.float32 and series.dim() == 2 and series.stride(1) == 1
+    B = series.shape[0]
+    n = int(series.shape[1] if n_valid is None else n_valid)
+    g = _chk(gaussian_sample, torch.float32, "gaussian_sample")
+    assert g.numel() == 500
+    dev_ = series.device
+    ws = int(lib.bpmf_threshold_workspace_bytes(B, n, half_window_samp, shift_samp))
+    workspace = torch.empty(max(ws, 256), dtype=torch.uint8, device=dev_)
+    count = torch.zeros(1, dtype=torch.int32, device=dev_)
+    o_series = torch.empty(capacity, dtype=torch.int32, device=dev_)
+    o_index = torch.empty(capacity, dtype=torch.int32, device=dev_)
+    o_value = torch.empty(capacity, dtype=torch.float32, device=dev_)
+    o_thr = torch.empty(capacity, dtype=torch.float32, device=dev_)
+    rc = lib.bpmf_detect_dev(series.data_ptr(), series.stride(0), B, g.data_ptr(), float(num_dev), n,
+                             int(half_window_samp), int(shift_samp), int(search_win), 1 if mode == "select" else 0,
+                             workspace.data_ptr(), workspace.numel(), count.data_ptr(), o_series.data_ptr(),
+                             o_index.data_ptr(), o_value.data_ptr(), o_thr.data_ptr(), capacity, _stream_ptr())
+    _lib.check(rc, "detect_dev")
+    k = int(count.item()) & 0xFFFFFFFF
+    if k > capacity:
+        raise _lib.BpmfError("detect_dev: %d candidates exceed capacity %d" % (k, capacity))
+    s_, i_ = o_series[:k].cpu().numpy(), o_index[:k].cpu().numpy()
+    v_, t_ = o_value[:k].cpu().numpy(), o_thr[:k].cpu().numpy()
+    order = np.lexsort((i_, s_))
+    return s_[order], i_[order], v_[order], t_[order]

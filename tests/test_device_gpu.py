@@ -36,6 +36,36 @@ def test_cc_to_threshold_without_leaving_the_device():
         assert np.abs(thr[t].cpu().numpy() - want).max() < 5e-6
 
 
+def test_detections_leave_the_device_as_a_compact_list():
+    """threshold + peak selection on the CC slab; only candidates are downloaded."""
+    tp, mv, w, d, planted = _synth.mf_case(6, 3, 2, 100, 60000, seed=24)
+    plan = dev.MatchedFilterPlan(6, 3, 2, 100, 60000, precision="fp32")
+    cc = plan.run(*(torch.from_numpy(a).cuda() for a in (tp, mv, w, d)))
+    cc_host = cc.cpu().numpy().copy()
+    wn = np.random.default_rng(1).standard_normal(500).astype(np.float32)
+    g = torch.from_numpy(wn).cuda()
+    half, shift, num_dev, win = 3000, 4500, 6.0, 150
+    for mode in ("above", "select"):
+        s_, i_, v_, t_ = dev.detect_dev(plan.cc, g, num_dev, half, shift, search_win=win, mode=mode, n_valid=plan.n_corr)
+        assert torch.equal(cc, plan.cc[:, : plan.n_corr]) and np.array_equal(cc.cpu().numpy(), cc_host)  # slab untouched
+        want = []
+        for t in range(6):
+            thr, _ = libc_numpy.time_dependent_threshold(cc_host[t], wn, num_dev, half, shift)
+            if mode == "above":
+                idx = np.nonzero(cc_host[t] > thr)[0]
+            else:
+                idx = np.nonzero(libc_numpy.select_cc_indexes(cc_host[t], thr, win))[0]
+            want += [(t, int(i)) for i in idx]
+        got = list(zip(s_.tolist(), i_.tolist()))
+        # thresholds agree to float32 round-off: allow candidates sitting exactly on the threshold to differ
+        assert set(got) == set(want) or len(set(got) ^ set(want)) <= 2, (mode, len(got), len(want))
+        assert np.allclose(v_, cc_host[s_, i_])
+        for t, i0 in planted.items():
+            assert (t, i0) in got
+    with pytest.raises(_lib.BpmfError):
+        dev.detect_dev(plan.cc, g, -100.0, half, shift, n_valid=plan.n_corr, capacity=16)  # everything is above
+
+
 def test_beam_plan_and_merge():
     f, tau, wp, ws = _synth.beam_case(120, 6, 2, 2, 8000, seed=23)
     args = [torch.from_numpy(a).cuda() for a in (f, tau.astype(np.int32), wp, ws)]
@@ -61,3 +91,34 @@ def test_caract_gpu_and_launch_counter(capfd):
 
     fmf.matched_filter(tp, mv, w, d, 1, check_zeros=False)
     assert lib.bpmf_launch_count() > before
+
+
+def test_prepare_traces_once_run_many_batches():
+    """BPMF loops template chunks over one day of data (similarity_search.py:783-790): the trace staging is
+    prepared once and reused by every batch / by a second template set, for each arithmetic."""
+    tp, mv, w, d, _ = _synth.mf_case(45, 4, 3, 300, 30000, seed=25)
+    want = cpu.matched_filter(tp, mv, w, d, 1)
+    dev_args = [torch.from_numpy(a).cuda() for a in (tp, mv, w, d)]
+    for prec, tol in (("fp32", 2e-6), ("fp16", 1e-4), ("fp16x3", 1e-5), ("auto", 1e-4)):
+        plan = dev.MatchedFilterPlan(45, 4, 3, 300, 30000, precision=prec, batch=16)
+        cc = plan.run(*dev_args)
+        assert np.abs(cc.cpu().numpy() - want).max() < tol, prec
+        # second pass on the same traces with permuted templates, without re-staging the traces
+        perm = torch.arange(44, -1, -1).cuda()
+        cc2 = plan.run(dev_args[0][perm].contiguous(), dev_args[1][perm].contiguous(),
+                       dev_args[2][perm].contiguous(), dev_args[3], prepared=True)
+        assert np.abs(cc2.cpu().numpy() - want[::-1]).max() < tol, prec
+
+
+def test_host_path_reuses_cached_buffers():
+    from seismic_bpmf_b200 import fast_matched_filter as fmf
+
+    lib = _lib.load()
+    tp, mv, w, d, _ = _synth.mf_case(150, 3, 2, 100, 20000, seed=26)  # > 128 templates: chunked on two streams
+    want = cpu.matched_filter(tp, mv, w, d, 1)
+    for _ in range(2):
+        got = fmf.matched_filter(tp, mv, w, d, 1, precision="fp32", check_zeros=False)
+        assert np.abs(got - want).max() < 2e-6
+    lib.bpmf_release_cache()
+    got = fmf.matched_filter(tp[:3], mv[:3], w[:3], d, 1, precision="fp32", check_zeros=False)
+    assert np.abs(got - want[:3]).max() < 2e-6
