@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=25.0)
+    ap.add_argument("--batch", type=int, default=0, help="templates per kernel launch at N > 1 (0 = default)")
     return ap.parse_args()
 
 
@@ -147,6 +148,18 @@ def make_inputs_device(torch, T, S, Cc, L, N, seed, device):
     return templates.contiguous(), moveouts.contiguous(), weights, data.contiguous(), planted
 
 
+def measured_traffic(kernel, T, S, Cc, L, N):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this exact
+    configuration (profiles/r1_traffic.json); None when the configuration was not captured."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    for rec in json.load(open(path)):
+        if rec["kernel"] == kernel and [rec["T"], rec["S"], rec["C"], rec["L"], rec["N"]] == [T, S, Cc, L, N]:
+            return rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    return None
+
+
 def algorithmic_bytes(T, S, Cc, L, N, n_corr):
     """compulsory traffic of one matched-filter pass."""
     return 4 * S * Cc * N + 4 * T * S * Cc * L + 8 * T * S * Cc + 4 * T * n_corr
@@ -233,7 +246,7 @@ def run_ours(args, rank, world, local_rank):
         planted = {}
     # N > 1: the per-rank pass runs in template batches so that the all-gather of one batch's CC slab
     # overlaps the kernels of the next one
-    batch = T if world == 1 else (128 if world <= 2 else 64)
+    batch = T if world == 1 else (args.batch or (128 if world <= 2 else 64))
     plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, precision=args.precision, device=device, batch=batch)
     n_corr = plan.n_corr
     units = T * S * Cc * n_corr  # per rank, per step
@@ -386,7 +399,8 @@ def run_ours(args, rank, world, local_rank):
         if plan_is_tensor(prec_name):
             mult = 3.0 if prec_name == "fp16x3" else 1.0
             roof = {"bound": "tensor", "achieved": tflops * mult, "peak": pk["tensor_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": tflops * mult / pk["tensor_tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": tflops * mult / pk["tensor_tflops_sustained"],
+                    "traffic": measured_traffic("mf_tc_kernel", T, S, Cc, L, N),
                     "peak_source": pk["source"] + " (sustained bf16 cuBLAS; fp16 runs at the same tensor rate)",
                     "algorithmic_tflops": tflops, "kernel_ms": kernel_ms, "kernel": "mf_tc_kernel"}
         else:

@@ -17,7 +17,7 @@
 //     the 8 lanes x 1 column of a template form ONE aligned 32-byte sector of cc_sum.  The
 //     whole-column part of the moveout, q = floor(moveout / 8), is an output address shift.
 //   * A (16 templates x 8 phases x Kc, up to 204 KB) stays RESIDENT in shared memory while the CTA
-//     sweeps a segment of 64 tiles (131 072 samples); B slices stream through a 2-stage bulk-copy
+//     sweeps a segment of 32 tiles (65 536 samples); B slices stream through a 2-stage bulk-copy
 //     ring.  Templates longer than one resident image are cut into K chunks (numerators add).
 //   * BPMF_MF_TC_FP16X3: both operands are split hi + lo (two fp16 = 22 mantissa bits) and three
 //     MMAs (hi*hi + hi*lo + lo*hi) accumulate into the same TMEM tile: fp32-grade numerators.
@@ -40,7 +40,7 @@ constexpr int TC_TPL = 16;          // templates per tile
 constexpr int TC_NCOL = 256;        // GEMM columns per tile (= 2048 samples)
 constexpr int TC_KC_MAX = 816;      // resident A, single pass: 128 x 816 fp16 = 208 896 B
 constexpr int TC_KC_MAX_SPLIT = 384; // resident A, hi + lo images: 128 x 384 x 2 x 2 = 196 608 B
-constexpr int TC_SEG_TILES = 64;    // tiles swept per resident A image
+constexpr int TC_SEG_TILES = 32;    // tiles swept per resident A image (65 536 samples)
 constexpr int TC_THREADS = 352;     // warp 0 A/B producer, warp 1 MMA, warps 2-9 epilogue, warp 10 rsqrt producer
 constexpr int TC_EPI_WARP0 = 2;
 constexpr int TC_NB = 2;            // trace-slice (B operand) stages
@@ -118,12 +118,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// L2 cache policies: the traces / rsqrt(energy) / A images stream through once per item (evict first), the
+// cc_sum lines are reduced into 48 times (once per channel) and must stay resident meanwhile (evict last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // TMA engine, non-tensor form: contiguous global -> shared bulk copy completing on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float *addr, float v, uint64_t policy) {
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(addr), "f"(v), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -201,7 +217,7 @@ __device__ __forceinline__ void tc_transpose4(float &v0, float &v1, float &v2, f
 // mode 2: everything valid; 1: per-element predicate; 0: nothing to write.
 __device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, float *const (&base)[4],
                                              const int (&i0)[4], const int (&lo)[4], const int (&hi)[4], int mode,
-                                             float ithr, float scale, bool b16, bool b8, int debug) {
+                                             float ithr, float scale, bool b16, bool b8, uint64_t policy, int debug) {
     float v[32];
     tc_ld32(taddr, v);
     if (debug & 1) mode = (v[0] == 12345.678f) ? mode : 0;  // triage: keep everything but the reductions
@@ -214,18 +230,23 @@ __device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, f
     }
 #pragma unroll
     for (int g = 0; g < 8; g++) tc_transpose4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], b16, b8);
-    if (mode == 2) {
+    if (mode == 2 && (debug & 4)) {  // triage: plain stores instead of reductions (wrong results)
 #pragma unroll
         for (int g = 0; g < 8; g++)
 #pragma unroll
-            for (int x = 0; x < 4; x++) atomicAdd(base[x] + 32 * g, v[4 * g + x]);
+            for (int x = 0; x < 4; x++) base[x][32 * g] = v[4 * g + x];
+    } else if (mode == 2) {
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) red_add_f32(base[x] + 32 * g, v[4 * g + x], policy);
     } else {
 #pragma unroll
         for (int g = 0; g < 8; g++)
 #pragma unroll
             for (int x = 0; x < 4; x++) {
                 const int i = i0[x] + 32 * g;
-                if (i >= lo[x] && i <= hi[x]) atomicAdd(base[x] + 32 * g, v[4 * g + x]);
+                if (i >= lo[x] && i <= hi[x]) red_add_f32(base[x] + 32 * g, v[4 * g + x], policy);
             }
     }
 }
@@ -280,6 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     if (warp == 0) {
         // ===================== producer: bulk copies of A images and trace slices ==================
         if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
             uint32_t n_item = 0, n_tile = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const TcItem im = tc_decode(p, it);
@@ -290,7 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 const uint8_t *src = p.aimg + ((size_t)(ch * p.MT + mt) * p.n_kc + im.kc) * p.a_bytes;
                 for (int off = 0; off < p.a_bytes; off += 16384) {
                     const int n = (p.a_bytes - off < 16384) ? (p.a_bytes - off) : 16384;
-                    bulk_g2s(a_s + off, src + off, (uint32_t)n, a_full);
+                    bulk_g2s(a_s + off, src + off, (uint32_t)n, a_full, pol);
                 }
                 n_item++;
                 const int t_begin = seg * p.seg_tiles;
@@ -300,8 +322,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                     mbar_wait(b_empty + s, ((n_tile / TC_NB) & 1) ^ 1);
                     const size_t d_off = (size_t)ch * p.dh_pitch + (size_t)tile * (8 * TC_NCOL) + (size_t)im.kc * p.Kc;
                     mbar_expect_tx(b_full + s, p.split ? 2 * b_bytes : b_bytes);
-                    bulk_g2s(b_s + s * p.b_stage_bytes, p.dh + d_off, b_bytes, b_full + s);
-                    if (p.split) bulk_g2s(b_s + s * p.b_stage_bytes + b_bytes, p.dh_lo + d_off, b_bytes, b_full + s);
+                    bulk_g2s(b_s + s * p.b_stage_bytes, p.dh + d_off, b_bytes, b_full + s, pol);
+                    if (p.split) bulk_g2s(b_s + s * p.b_stage_bytes + b_bytes, p.dh_lo + d_off, b_bytes, b_full + s, pol);
                 }
             }
         }
@@ -351,6 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     } else if (warp == TC_EPI_WARP0 + 8) {
         // ===================== rsqrt(energy) producer: 32-column slices for the epilogue ===========
         if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
             uint32_t n_chunk = 0;  // per half: chunks issued so far
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const TcItem im = tc_decode(p, it);
@@ -369,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                             mbar_wait(inv_empty + h * TC_NI + slot, par);
                             mbar_expect_tx(full, TC_INV_SLOT * 4);
                             bulk_g2s(inv_s + (h * TC_NI + slot) * TC_INV_SLOT,
-                                     ci + 8 * ((size_t)tile * TC_NCOL + h * 128 + chunk * 32), TC_INV_SLOT * 4, full);
+                                     ci + 8 * ((size_t)tile * TC_NCOL + h * 128 + chunk * 32), TC_INV_SLOT * 4, full, pol);
                         }
                     }
                 }
@@ -380,6 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
         const int half = (warp - TC_EPI_WARP0) >> 2;       // which 128 columns of the tile
         const int row = quarter * 32 + lane;               // A row == TMEM lane
+        const uint64_t red_policy = l2_policy_evict_last();
         uint32_t n_tile = 0, n_chunk = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const TcItem im = tc_decode(p, it);
@@ -445,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                         ci0[x] = (int)(o + lane);
                     }
                     tc_epi_chunk(taddr + (uint32_t)(chunk * 32), inv, cbase, ci0, tlo, thi, mode, ithr, scale, b16, b8,
-                                 p.debug);
+                                 red_policy, p.debug);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(inv_empty + half * TC_NI + slot);
                 }
@@ -710,7 +734,8 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     p.b_slice_bytes = g.b_slice_bytes; p.b_stage_bytes = g.b_stage_bytes;
     p.n_tiles = g.n_tiles;
     p.seg_tiles = TC_SEG_TILES;
-    p.n_seg = (g.n_tiles + TC_SEG_TILES - 1) / TC_SEG_TILES;
+    if (const char *sg = getenv("BPMF_TC_SEG_TILES")) p.seg_tiles = std::max(1, atoi(sg));  // tuning experiments
+    p.n_seg = (g.n_tiles + p.seg_tiles - 1) / p.seg_tiles;
     {
         const char *dbg = getenv("BPMF_TC_DEBUG");
         p.debug = dbg ? atoi(dbg) : 0;
