@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libbpmf_b200.so")
+# BPMF_B200_LIB overrides the library path (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("BPMF_B200_LIB") or os.path.join(HERE, "lib", "libbpmf_b200.so")
 
 OK = 0
 MF_AUTO, MF_FP32, MF_TC_FP16, MF_TC_FP16X3 = 0, 1, 2, 3
