@@ -364,6 +364,22 @@ extern "C" int bpmf_matched_filter(const float *templates, const int *moveouts, 
     const size_t pitch = network_sum ? align_up(n_corr, 64) : 0;
     const size_t row_elems = network_sum ? pitch : n_corr * SC;
 
+    // AUTO is resolved once, on the host copy of the weights (same rule as mf_auto_precision), so that the
+    // chunk loop below never synchronises
+    if (precision == BPMF_MF_AUTO) {
+        MfShape sh0 = make_shape(L, N, 1, S, C, step, normalize ? 1 : 0, network_sum ? 1 : 0);
+        if (resolve_precision(sh0, precision) == BPMF_MF_TC_FP16) {
+            double w2max = 0.0;
+            for (size_t t = 0; t < T; t++) {
+                double a = 0.0;
+                for (size_t q = 0; q < SC; q++) a += (double)weights[t * SC + q] * (double)weights[t * SC + q];
+                w2max = std::max(w2max, a);
+            }
+            precision = (2.6e-3 * sqrt(w2max) / sqrt((double)L) < 6e-5) ? BPMF_MF_TC_FP16 : BPMF_MF_TC_FP16X3;
+        }
+    }
+
+
     int dev = 0;
     BPMF_CUDA(cudaGetDevice(&dev));
     // one host-path call at a time per device uses the cache; a concurrent caller gets private buffers
@@ -413,9 +429,10 @@ extern "C" int bpmf_matched_filter(const float *templates, const int *moveouts, 
     MF_TRY(cudaMemGetInfo(&free_b, &total_b));
     for (int i = 2; i < 12; i++) free_b += c->cap[i];  // chunk buffers already held by the cache are reusable
 
-    // chunk size: ~8 chunks for overlap when T is large, bounded by half of the free memory
+    // chunk size: ~16 chunks when T is large (the first chunk's kernels are the only ones the device->host
+    // copies cannot hide behind), bounded by half of the free memory
     size_t Tc = T;
-    if (T >= 128) Tc = align_up((T + 7) / 8, 16);
+    if (T >= 64) Tc = std::max<size_t>(32, align_up((T + 15) / 16, 16));
     auto need = [&](size_t tc) {
         return 2 * (sizeof(float) * tc * row_elems + sizeof(float) * tc * SC * L + 8 * tc * SC +
                     bpmf_mf_template_workspace_bytes(L, N, tc, S, C, step, normalize, network_sum, precision));
