@@ -228,3 +228,40 @@ def test_large_shape_properties():
         assert np.abs(res[p] - ref).max() < _tol(p, L, w), p
     sub = cpu.matched_filter(tp[:4], mv[:4], w[:4], d, 1)
     assert np.abs(ref[:4] - sub).max() < 2e-6
+
+
+def test_randomised_shape_sweep():
+    """Seeded sweep over ragged shapes, moveout ranges (negative, beyond one tile, non multiples of 8),
+    sparse weights and short traces: every arithmetic against the oracle, zeros in the same places."""
+    rng = np.random.default_rng(777)
+    for case in range(24):
+        T = int(rng.integers(1, 40))
+        S = int(rng.integers(1, 5))
+        C = int(rng.integers(1, 4))
+        L = int(rng.choice([8, 9, 16, 31, 64, 100, 257, 800, 820, 1000]))
+        N = int(L + rng.integers(0, 6000))
+        data = rng.standard_normal((S, C, N)).astype(np.float32)
+        if case % 3 == 0 and N > 50:
+            a = int(rng.integers(0, N - 10))
+            data[:, :, a: a + int(rng.integers(1, N // 3 + 2))] = 0.0
+        tp = rng.standard_normal((T, S, C, L)).astype(np.float32) * float(10.0 ** rng.integers(-3, 4))
+        span = max(1, (N - L) // 2)
+        mv = rng.integers(-min(span, 300), min(span, 3000) + 1, size=(T, S, C)).astype(np.int32)
+        w = rng.random((T, S, C)).astype(np.float32)
+        w[rng.random((T, S, C)) < 0.3] = 0.0
+        if case % 4 == 1:
+            w[0] = 0.0
+        nrm = w.sum(axis=(1, 2), keepdims=True)
+        nrm[nrm == 0] = 1.0
+        w = (w / nrm).astype(np.float32)
+        want = cpu.matched_filter(tp, mv, w, data, 1)
+        for prec in _precisions(L):
+            got = fmf.matched_filter(tp, mv, w, data, 1, precision=prec, check_zeros=False)
+            assert got.shape == want.shape
+            err = float(np.abs(got - want).max()) if want.size else 0.0
+            assert err < _tol(prec, L, w), (case, prec, (T, S, C, L, N), err)
+            assert np.isfinite(got).all()
+            # exact zeros (out-of-range outputs, dead windows) coincide, up to windows whose energy sits on the
+            # 1e-6 stability guard (edges of a zero gap), where float round-off may decide either way
+            mismatch = np.count_nonzero((got == 0) != (want == 0))
+            assert mismatch <= max(2, want.size // 500), (case, prec, mismatch)
