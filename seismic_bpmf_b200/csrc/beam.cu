@@ -25,6 +25,7 @@ constexpr int B_R = 8;                    // samples per thread
 constexpr int B_TT = B_THREADS * B_R;     // 2048-sample tile
 constexpr int B_KB = 8;                   // sources per register block
 constexpr int B_CAP = B_TT + 1024;        // staged row segment (floats)
+constexpr int B_NBUF = 3;                 // row segments in flight
 
 // U rows have a pitch that is a multiple of 4 floats (16-byte aligned rows for the float4 staging of the
 // beam kernel); the pad beyond N is zero.
@@ -111,8 +112,8 @@ __global__ void __launch_bounds__(B_THREADS, 2)
                 const int *__restrict__ thi, size_t K, int S, int P, long long N, long long pitch, int strict,
                 size_t k_chunk, unsigned long long *__restrict__ keys, float *__restrict__ beam) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *buf0 = reinterpret_cast<float *>(smem_raw);                 // 2 x B_CAP (double buffer)
-    int *tau_s = reinterpret_cast<int *>(buf0 + 2 * B_CAP);            // B_KB * S * P
+    float *buf0 = reinterpret_cast<float *>(smem_raw);                 // B_NBUF x B_CAP (ring of row segments)
+    int *tau_s = reinterpret_cast<int *>(buf0 + B_NBUF * B_CAP);       // B_KB * S * P
     float *beta_s = reinterpret_cast<float *>(tau_s + B_KB * S * P);   // B_KB * S
     int *wlo_s = reinterpret_cast<int *>(beta_s + B_KB * S);           // S * P: window start per (station, phase)
     int *wide_s = wlo_s + S * P;                                       // S * P: 1 = moveouts do not fit one window
@@ -170,18 +171,24 @@ __global__ void __launch_bounds__(B_THREADS, 2)
 #pragma unroll
             for (int r = 0; r < B_R; r++) acc[kk][r] = 0.f;
 
-        // software pipeline over (station, phase): row sp+1 streams in with cp.async while row sp is used
-        if (wide_s[0] != 2) beam_stage_async(buf0, U, t0 + wlo_s[0], pitch, tid);
-        cp_async_commit();
+        // software pipeline over (station, phase): rows sp+1 and sp+2 stream in with cp.async while row sp is
+        // used (3-slot ring, ONE barrier per row: it publishes row sp and retires row sp-1, whose slot is then
+        // refilled with row sp+2)
+#pragma unroll
+        for (int pre = 0; pre < 2; pre++) {
+            if (pre < SP && wide_s[pre] != 2)
+                beam_stage_async(buf0 + pre * B_CAP, U + (size_t)pre * pitch, t0 + wlo_s[pre], pitch, tid);
+            cp_async_commit();
+        }
         for (int sp = 0; sp < SP; sp++) {
             const int s = sp / P;
-            float *buf = buf0 + (sp & 1) * B_CAP;
-            if (sp + 1 < SP && wide_s[sp + 1] != 2)
-                beam_stage_async(buf0 + ((sp + 1) & 1) * B_CAP, U + (size_t)(sp + 1) * pitch, t0 + wlo_s[sp + 1], pitch,
-                                 tid);
-            cp_async_commit();
+            float *buf = buf0 + (sp % B_NBUF) * B_CAP;
             cp_async_wait<1>();  // row sp has landed (row sp+1 may still be in flight)
             __syncthreads();
+            if (sp + 2 < SP && wide_s[sp + 2] != 2)
+                beam_stage_async(buf0 + ((sp + 2) % B_NBUF) * B_CAP, U + (size_t)(sp + 2) * pitch, t0 + wlo_s[sp + 2],
+                                 pitch, tid);
+            cp_async_commit();
             const int wide = wide_s[sp];
             if (wide == 0) {
                 // straight-line code over the block's 8 sources: (offset, weight) pairs come as broadcast
@@ -227,7 +234,6 @@ __global__ void __launch_bounds__(B_THREADS, 2)
                     for (int r = 0; r < B_R; r++) acc[kk][r] = fmaf(b, src[B_THREADS * r], acc[kk][r]);
                 }
             }
-            __syncthreads();  // everyone is done with buf before it is refilled two rows later
         }
         cp_async_wait<0>();
 
@@ -288,7 +294,7 @@ __global__ void beam_merge_kernel(float *__restrict__ ma, int *__restrict__ aa,
 }
 
 static size_t beam_smem_bytes(size_t S, size_t P) {
-    return sizeof(float) * 2 * B_CAP + sizeof(int) * B_KB * S * P + sizeof(float) * B_KB * S +
+    return sizeof(float) * B_NBUF * B_CAP + sizeof(int) * B_KB * S * P + sizeof(float) * B_KB * S +
            2 * sizeof(int) * (S * P + 1) + sizeof(int2) * B_KB * S * P + 16;
 }
 
