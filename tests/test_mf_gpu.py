@@ -265,3 +265,24 @@ def test_randomised_shape_sweep():
             # 1e-6 stability guard (edges of a zero gap), where float round-off may decide either way
             mismatch = np.count_nonzero((got == 0) != (want == 0))
             assert mismatch <= max(2, want.size // 500), (case, prec, mismatch)
+
+
+def test_large_dynamic_range_traces():
+    """A transient 1e5 times the noise level (a nearby large earthquake) must not degrade the CC of the
+    quiet windows: the fp16 operands are scaled per channel by a power of two of the channel maximum,
+    and stay in the normal range over ~9 decades."""
+    tp, mv, w, d, planted = _synth.mf_case(6, 4, 3, 400, 60000, seed=61, zero_gap=False)
+    d = d.copy()
+    d[:, :, 30000:30050] *= 1.0e5
+    d[1, 0, 45000] = 3.0e7
+    want = cpu.matched_filter(tp, mv, w, d, 1)
+    for prec in _precisions(400):
+        got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
+        assert np.isfinite(got).all()
+        assert np.abs(got - want).max() < _tol(prec, 400, w), prec
+        for t, i0 in planted.items():
+            assert abs(got[t, i0] - w[t].sum()) < _tol(prec, 400, w) + 1e-6
+    # raw counts (no normalisation, amplitudes ~1e6) and tiny physical units (~1e-7) give the same CC
+    for gain in (1.0e6, 1.0e-3):
+        got = fmf.matched_filter(tp * np.float32(gain), mv, w, d * np.float32(gain), 1, check_zeros=False)
+        assert np.abs(got - want).max() < TOL
