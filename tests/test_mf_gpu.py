@@ -269,20 +269,22 @@ def test_randomised_shape_sweep():
 
 def test_large_dynamic_range_traces():
     """A transient 1e5 times the noise level (a nearby large earthquake) must not degrade the CC of the
-    quiet windows: the fp16 operands are scaled per channel by a power of two of the channel maximum,
-    and stay in the normal range over ~9 decades."""
-    tp, mv, w, d, planted = _synth.mf_case(6, 4, 3, 400, 60000, seed=61, zero_gap=False)
+    quiet windows: the fp16 operands are scaled per channel by a power of two of the channel maximum and
+    stay in the normal range over ~9 decades.  Checked against the float64 brute force (window-local sums):
+    a global float64 prefix sum -- what mf_oracle.c and upstream use -- loses ~1e-4 of the energy of
+    every window after a 3e7 spike, the block-local prefix sums of the CUDA pre-pass do not."""
+    tp, mv, w, d, planted = _synth.mf_case(3, 3, 2, 200, 24000, seed=61, zero_gap=False)
     d = d.copy()
-    d[:, :, 30000:30050] *= 1.0e5
-    d[1, 0, 45000] = 3.0e7
-    want = cpu.matched_filter(tp, mv, w, d, 1)
-    for prec in _precisions(400):
+    d[:, :, 12000:12050] *= 1.0e5
+    d[1, 0, 18000] = 3.0e7
+    want = numpy_ref.matched_filter(tp, mv, w, d, 1)
+    for prec in _precisions(200):
         got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
         assert np.isfinite(got).all()
-        assert np.abs(got - want).max() < _tol(prec, 400, w), prec
+        assert np.abs(got - want).max() < _tol(prec, 200, w), prec
         for t, i0 in planted.items():
-            assert abs(got[t, i0] - w[t].sum()) < _tol(prec, 400, w) + 1e-6
-    # raw counts (no normalisation, amplitudes ~1e6) and tiny physical units (~1e-7) give the same CC
+            assert abs(got[t, i0] - w[t].sum()) < _tol(prec, 200, w) + 1e-6
+    # raw counts (no normalisation, amplitudes ~1e6) and tiny physical units (~1e-3) give the same CC
     for gain in (1.0e6, 1.0e-3):
         got = fmf.matched_filter(tp * np.float32(gain), mv, w, d * np.float32(gain), 1, check_zeros=False)
         assert np.abs(got - want).max() < TOL
