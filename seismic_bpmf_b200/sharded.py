@@ -35,17 +35,75 @@ def _mf_compute_cuda(templates, moveouts, weights, data, step, normalize, precis
                                   network_sum=True, precision=precision)
 
 
+def _matched_filter_sharded_overlapped(templates, moveouts, weights, data, step, normalize, precision, group,
+                                       batch):
+    """CUDA path with the exchange hidden behind the compute: the local shard runs in template batches and
+    every finished batch is pushed to the peers' buffers by the copy engines (PeerSlabGather) while the next
+    batch computes; the batches are then laid out in template order."""
+    from . import device as dev
+
+    rank, world = _world(group)
+    T, S, C, L = templates.shape
+    lo, hi = shard_bounds(T, rank, world)
+    rows = (T + world - 1) // world  # longest shard: every rank runs the same number of batches
+    plan = dev.MatchedFilterPlan(max(hi - lo, 1), S, C, L, data.shape[-1], step=step, normalize=normalize,
+                                 precision=precision, device=data.device, batch=batch)
+    n_corr, pitch = plan.n_corr, plan.pitch
+    gather = PeerSlabGather(batch * pitch, data.device, group)
+    out = torch.empty((T, n_corr), dtype=torch.float32, device=data.device)
+    tp, mv, w = templates[lo:hi].contiguous(), moveouts[lo:hi].contiguous(), weights[lo:hi].contiguous()
+    if hi > lo:
+        plan.prepare(data)
+    empty = torch.zeros(0, dtype=torch.float32, device=data.device)
+    pending = []
+    for b, t0 in enumerate(range(0, rows, batch)):
+        n_here = max(0, min(batch, (hi - lo) - t0))
+        if b >= 2:  # buffer b % 2 is about to be refilled: lay out the batch it still holds
+            _scatter_gathered(out, gather, *pending.pop(0), T, world, pitch, n_corr)
+        if n_here > 0:
+            plan.run_batch(tp, mv, w, data, t0, n_here)
+            gather.push(b % 2, plan.cc[t0: t0 + n_here].reshape(-1))
+        else:
+            gather.push(b % 2, empty)  # short shard: still take part in the batch barrier
+        pending.append((b % 2, t0))
+    for item in pending:
+        _scatter_gathered(out, gather, *item, T, world, pitch, n_corr)
+    torch.cuda.current_stream().wait_stream(gather.stream)
+    return out
+
+
+def _scatter_gathered(out, gather, buf, t0, T, world, pitch, n_corr):
+    """Copy batch rows [t0, t0 + batch) of every rank's shard from gather buffer ``buf`` into template order
+    (on the gather's ordering stream, behind that batch's barrier)."""
+    with torch.cuda.stream(gather.stream):
+        view = gather.local[buf].view(world, -1)
+        for r in range(world):
+            a, b_ = shard_bounds(T, r, world)
+            n = max(0, min(b_ - a - t0, view.shape[1] // pitch))
+            if n > 0:
+                out[a + t0: a + t0 + n] = view[r, : n * pitch].view(n, pitch)[:, :n_corr]
+
+
 def matched_filter_sharded(templates, moveouts, weights, data, step=1, normalize="short",
-                           precision="auto", group=None, gather=True, compute=None):
+                           precision="auto", group=None, gather=True, compute=None, overlap=True, batch=64):
     """Template-sharded matched filter.
 
     Every rank passes the FULL (T,S,C,L) templates / (T,S,C) moveouts, weights and the (S,C,N)
     traces (torch tensors on its own device).  Returns the (T, n_corr) CC sums on every rank when
-    ``gather`` is true, else ``(local_cc, (t_lo, t_hi))``.
+    ``gather`` is true, else ``(local_cc, (t_lo, t_hi))``.  On CUDA with more than one rank the exchange is
+    overlapped with the compute (``overlap``); otherwise one NCCL / gloo all-gather follows the compute.
     """
     rank, world = _world(group)
     T = templates.shape[0]
     lo, hi = shard_bounds(T, rank, world)
+    if gather and overlap and compute is None and world > 1 and data.is_cuda:
+        try:
+            return _matched_filter_sharded_overlapped(templates, moveouts, weights, data, step, normalize,
+                                                      precision, dist.group.WORLD if group is None else group, batch)
+        except (ImportError, AttributeError, RuntimeError) as exc:  # symmetric memory unavailable
+            import warnings
+
+            warnings.warn("overlapped exchange unavailable (%s); falling back to an NCCL all-gather" % (exc,))
     compute = compute or _mf_compute_cuda
     n_corr = (data.shape[-1] - templates.shape[-1]) // step + 1
     if hi > lo:
