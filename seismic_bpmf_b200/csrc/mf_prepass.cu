@@ -3,7 +3,7 @@
 //     sum_square_templates on the host before its native call [UPSTREAM-UNVERIFIED])
 //   * per-template valid output range from weights + moveouts
 //   * per-channel sliding window energy  E[ch][j] = sum_{k<L} d[ch][j+k]^2, j in [0, N-L]
-//     accumulated in float64 block-local prefix sums (SURVEY section 7 "Sliding energy in FP32").
+//     accumulated in float64 segment-local sums, free of cancellation (SURVEY section 7 "Sliding energy in FP32").
 // All HBM-bound streaming kernels: reads 4*S*C*N, writes 4*S*C*(N-L+1) (x2 for normalize=full).
 #include "common.cuh"
 
@@ -63,80 +63,145 @@ __global__ void mf_bounds_kernel(const int *__restrict__ moveouts, const float *
 }
 
 // ---------------------------------------------------------------- sliding window energy
+// E[j] = sum_{k<L} d[j+k]^2 without any cancellation: the block's samples are cut into segments of L
+// samples; with SUF[i] = sum from i to the end of i's segment and PRE[i] = sum from the start of i's
+// segment to i, a window starting at j = m*L + r is the tail of segment m plus the first r samples of
+// segment m+1:  E[j] = SUF[j] + (r ? PRE[j+L-1] : 0).  Only sums of at most L same-sign terms are ever
+// formed (float64), so a 1e7 x noise transient does not leak into the energy of the quiet windows after
+// it, which a running prefix-sum difference (what mf_oracle.c and upstream do) cannot guarantee.
 constexpr int EN_THREADS = 256;
-constexpr int EN_BJ = 4096;  // window starts per block
+constexpr int EN_R = 16;
+constexpr int EN_BJ = EN_THREADS * EN_R;  // window starts per block
 
-__device__ __forceinline__ double block_exclusive_scan(double v, double *warp_tot, double *total) {
+// Segmented scan over the threads of the block.  Every thread contributes (tail, flag): the sum of its
+// run after the last segment start inside the run, and whether the run contains a segment start.
+// Returns the carry: the sum of the elements between the closest preceding segment start and the
+// thread's own run.
+__device__ __forceinline__ double block_segmented_carry(double tail, bool flag, double *warp_val, int *warp_flag) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double inc = v;
+    double s = tail;
+    int f = flag ? 1 : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const double u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
+        const double us = __shfl_up_sync(0xffffffffu, s, o);
+        const int uf = __shfl_up_sync(0xffffffffu, f, o);
+        if (lane >= o) {
+            if (!f) s += us;
+            f |= uf;
+        }
     }
-    if (lane == 31) warp_tot[wid] = inc;
+    if (lane == 31) { warp_val[wid] = s; warp_flag[wid] = f; }
+    double ex_s = __shfl_up_sync(0xffffffffu, s, 1);
+    int ex_f = __shfl_up_sync(0xffffffffu, f, 1);
+    if (lane == 0) { ex_s = 0.0; ex_f = 0; }
     __syncthreads();
-    double base = 0.0, tot = 0.0;
+    double ws = 0.0;  // aggregate of the warps before this one
 #pragma unroll
     for (int w = 0; w < EN_THREADS / 32; w++) {
-        const double x = warp_tot[w];
-        if (w < wid) base += x;
-        tot += x;
+        if (w < wid) ws = warp_flag[w] ? warp_val[w] : ws + warp_val[w];
     }
     __syncthreads();
-    *total = tot;
-    return base + inc - v;
+    return ex_f ? ex_s : ws + ex_s;
+}
+
+// REV = false: out[i] = sum of x from the start of i's segment to i (segments of L samples from 0);
+// REV = true:  out[i] = sum of x from i to the end of i's segment (or of the span); x = d^2 or d.
+template <bool REV, bool SQ>
+__device__ __forceinline__ void segment_sums(const float *__restrict__ d, size_t span, size_t L,
+                                             double *__restrict__ out, double *warp_val, int *warp_flag) {
+    const size_t run = (span + EN_THREADS - 1) / EN_THREADS;
+    const size_t k = REV ? (size_t)(EN_THREADS - 1 - threadIdx.x) : (size_t)threadIdx.x;
+    const size_t a = (k * run < span) ? k * run : span;
+    const size_t b = (a + run < span) ? a + run : span;
+    double tail = 0.0;
+    bool flag = false;
+    if (!REV) {
+        size_t pos = a % L;
+        for (size_t i = a; i < b; i++) {
+            if (pos == 0) { tail = 0.0; flag = true; }
+            if (++pos == L) pos = 0;
+            const double v = (double)d[i];
+            tail += SQ ? v * v : v;
+        }
+    } else {
+        size_t rem = b % L;  // (i + 1) % L for i = b - 1
+        for (size_t i = b; i-- > a;) {
+            if (rem == 0 || i == span - 1) { tail = 0.0; flag = true; }
+            if (rem == 0) rem = L;
+            rem--;
+            const double v = (double)d[i];
+            tail += SQ ? v * v : v;
+        }
+    }
+    double r = block_segmented_carry(tail, flag, warp_val, warp_flag);
+    if (!REV) {
+        size_t pos = a % L;
+        for (size_t i = a; i < b; i++) {
+            if (pos == 0) r = 0.0;
+            if (++pos == L) pos = 0;
+            const double v = (double)d[i];
+            r += SQ ? v * v : v;
+            out[i] = r;
+        }
+    } else {
+        size_t rem = b % L;
+        for (size_t i = b; i-- > a;) {
+            if (rem == 0 || i == span - 1) r = 0.0;
+            if (rem == 0) rem = L;
+            rem--;
+            const double v = (double)d[i];
+            r += SQ ? v * v : v;
+            out[i] = r;
+        }
+    }
 }
 
 // RSQRT: write 1/sqrt(E) (0 where E <= 0) instead of E -- the per-column factor of the tensor path.
-// phase8: write phase-major, out[ch][j % 8][j / 8] with rows of out_pitch elements (tensor path).
+// phase8: write phase-major, out[ch][j % 8][j / 8] with rows of out_pitch elements.
 template <bool FULL, bool RSQRT>
 __global__ void __launch_bounds__(EN_THREADS)
     mf_energy_kernel(const float *__restrict__ data, size_t N, size_t L, size_t n_win, size_t out_pitch,
                      int phase8, float *__restrict__ energy, float *__restrict__ mean) {
     extern __shared__ double sm[];
-    __shared__ double warp_tot[EN_THREADS / 32];
+    __shared__ double warp_val[EN_THREADS / 32];
+    __shared__ int warp_flag[EN_THREADS / 32];
     const size_t ch = blockIdx.y;
     const size_t j0 = (size_t)blockIdx.x * EN_BJ;
     if (j0 >= n_win) return;
     const size_t nj = (n_win - j0 < (size_t)EN_BJ) ? (n_win - j0) : (size_t)EN_BJ;
     const size_t span = nj + L - 1;  // data samples [j0, j0 + span)
     const float *d = data + ch * N + j0;
-    double *P2 = sm;                                // span + 1 exclusive prefix of d^2
-    double *P1 = sm + (FULL ? span + 1 : 0);        // span + 1 exclusive prefix of d
+    double *P2 = sm;                         // span sums of d^2
+    double *P1 = sm + (FULL ? span : 0);     // span sums of d
 
-    const size_t run = (span + EN_THREADS - 1) / EN_THREADS;
-    const size_t a = (size_t)threadIdx.x * run;
-    const size_t b = (a + run < span) ? a + run : span;
-    double s2 = 0.0, s1 = 0.0;
-    for (size_t i = a; i < b; i++) {
-        const double v = (double)d[i];
-        s2 += v * v;
-        if (FULL) s1 += v;
-    }
-    double tot2, tot1 = 0.0;
-    double r2 = block_exclusive_scan(s2, warp_tot, &tot2);
-    double r1 = 0.0;
-    if (FULL) r1 = block_exclusive_scan(s1, warp_tot, &tot1);
-    for (size_t i = a; i < b; i++) {
-        const double v = (double)d[i];
-        P2[i] = r2;
-        r2 += v * v;
-        if (FULL) { P1[i] = r1; r1 += v; }
-    }
-    if (threadIdx.x == 0) {
-        P2[span] = tot2;
-        if (FULL) P1[span] = tot1;
+    // tails of the segments (kept in registers), then the heads of the next segments in the same arrays
+    double suf2[EN_R], suf1[EN_R];
+    segment_sums<true, true>(d, span, L, P2, warp_val, warp_flag);
+    if (FULL) segment_sums<true, false>(d, span, L, P1, warp_val, warp_flag);
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < EN_R; m++) {
+        const size_t j = (size_t)threadIdx.x + (size_t)EN_THREADS * m;
+        suf2[m] = (j < nj) ? P2[j] : 0.0;
+        suf1[m] = (FULL && j < nj) ? P1[j] : 0.0;
     }
     __syncthreads();
+    segment_sums<false, true>(d, span, L, P2, warp_val, warp_flag);
+    if (FULL) segment_sums<false, false>(d, span, L, P1, warp_val, warp_flag);
+    __syncthreads();
+
     float *e = energy + (phase8 ? ch * 8 * out_pitch : ch * out_pitch + j0);
-    float *m = FULL ? mean + ch * out_pitch + j0 : nullptr;
-    for (size_t j = threadIdx.x; j < nj; j += EN_THREADS) {
-        double ss = P2[j + L] - P2[j];
+    float *mo = FULL ? mean + ch * out_pitch + j0 : nullptr;
+#pragma unroll
+    for (int m = 0; m < EN_R; m++) {
+        const size_t j = (size_t)threadIdx.x + (size_t)EN_THREADS * m;
+        if (j >= nj) continue;
+        const bool whole = (j % L) == 0;  // the window is exactly one segment
+        double ss = suf2[m] + (whole ? 0.0 : P2[j + L - 1]);
         if (FULL) {
-            const double mu = (P1[j + L] - P1[j]) / (double)L;
+            const double mu = (suf1[m] + (whole ? 0.0 : P1[j + L - 1])) / (double)L;
             ss -= (double)L * mu * mu;
-            m[j] = (float)mu;
+            mo[j] = (float)mu;
         }
         const size_t jg = j0 + j;
         const size_t o = phase8 ? (jg & 7) * out_pitch + (jg >> 3) : j;

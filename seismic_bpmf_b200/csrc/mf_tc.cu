@@ -41,8 +41,12 @@ constexpr int TC_NCOL = 256;        // GEMM columns per tile (= 2048 samples)
 constexpr int TC_KC_MAX = 816;      // resident A, single pass: 128 x 816 fp16 = 208 896 B
 constexpr int TC_KC_MAX_SPLIT = 384; // resident A, hi + lo images: 128 x 384 x 2 x 2 = 196 608 B
 constexpr int TC_SEG_TILES = 32;    // tiles swept per resident A image (65 536 samples)
-constexpr int TC_THREADS = 352;     // warp 0 A/B producer, warp 1 MMA, warps 2-9 epilogue, warp 10 rsqrt producer
+#ifndef TC_EPI_WARPS
+#define TC_EPI_WARPS 16             // 8 or 16: with 16, two warps share each (lane quarter, tile half) and take alternate chunks
+#endif
 constexpr int TC_EPI_WARP0 = 2;
+constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS + 1);  // warp 0 A/B producer, warp 1 MMA, epilogue warps, rsqrt producer
+constexpr int TC_EPI_SUBS = TC_EPI_WARPS / 8;
 constexpr int TC_NB = 2;            // trace-slice (B operand) stages
 constexpr int TC_NI = 5;            // rsqrt(energy) slots per tile half (32 columns each)
 constexpr int TC_INV_SLOT = 264;    // floats per slot: 8 * 32 columns + 8 (row delays reach 14)
@@ -191,36 +195,48 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// 4x4 transpose between the template index of a lane (lane >> 3) and the column index within a
-// group of four registers, by two butterfly exchanges.  Before: lane (a, r), register x = template a,
-// column 4g+x.  After: lane (a, r), register x = template x, column 4g+a -- so register x of the 32
-// lanes is 32 CONSECUTIVE outputs (offset 8*(4g+a) + r = 32g + lane) of template x.
-__device__ __forceinline__ void tc_transpose4(float &v0, float &v1, float &v2, float &v3, bool b16, bool b8) {
-    {   // exchange across lane bit 16 <-> register bit 1: pairs (0,2) and (1,3)
-        float s0 = b16 ? v0 : v2, s1 = b16 ? v1 : v3;
-        s0 = __shfl_xor_sync(0xffffffffu, s0, 16);
-        s1 = __shfl_xor_sync(0xffffffffu, s1, 16);
-        if (b16) { v0 = s0; v1 = s1; } else { v2 = s0; v3 = s1; }
+// 4x4 transpose between two lane bits (masks HI, LO) and the index within a group of four registers,
+// by two butterfly exchanges: afterwards register x of the lane whose two bits read y holds what
+// register y of the lane whose two bits read x held.
+template <int HI, int LO>
+__device__ __forceinline__ void tc_transpose4(float &v0, float &v1, float &v2, float &v3, bool bhi, bool blo) {
+    {   // exchange across lane bit HI <-> register bit 1: pairs (0,2) and (1,3)
+        float s0 = bhi ? v0 : v2, s1 = bhi ? v1 : v3;
+        s0 = __shfl_xor_sync(0xffffffffu, s0, HI);
+        s1 = __shfl_xor_sync(0xffffffffu, s1, HI);
+        if (bhi) { v0 = s0; v1 = s1; } else { v2 = s0; v3 = s1; }
     }
-    {   // exchange across lane bit 8 <-> register bit 0: pairs (0,1) and (2,3)
-        float s0 = b8 ? v0 : v1, s1 = b8 ? v2 : v3;
-        s0 = __shfl_xor_sync(0xffffffffu, s0, 8);
-        s1 = __shfl_xor_sync(0xffffffffu, s1, 8);
-        if (b8) { v0 = s0; v2 = s1; } else { v1 = s0; v3 = s1; }
+    {   // exchange across lane bit LO <-> register bit 0: pairs (0,1) and (2,3)
+        float s0 = blo ? v0 : v1, s1 = blo ? v2 : v3;
+        s0 = __shfl_xor_sync(0xffffffffu, s0, LO);
+        s1 = __shfl_xor_sync(0xffffffffu, s1, LO);
+        if (blo) { v0 = s0; v2 = s1; } else { v1 = s0; v3 = s1; }
     }
 }
 
-// one 32-column chunk of the epilogue: TMEM -> registers -> normalise -> transpose -> red.global.add
-// in whole 128-byte runs.  inv points at this row's first rsqrt(energy) value of the chunk (column c
-// lives 8*c floats on); base[x] points at output 8*(first column of the chunk - q_x) + lane of the
-// warp's x-th template; i0[x] is that output's index, valid iff lo[x] <= i <= hi[x].
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d, uint64_t policy) {
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b),
+                 "f"(c), "f"(d), "l"(policy)
+                 : "memory");
+}
+
+// one 32-column chunk of the epilogue: TMEM -> registers -> normalise -> transpose -> red.global.add.
+// inv points at this row's first rsqrt(energy) value of the chunk (column c lives 8*c floats on).
+// Lane (a, r) [a = lane >> 3: template of the warp, r = lane & 7: phase] holds columns c = 0..31 of its
+// row; output index of (a, c, r) = 8*(column - q_a) + r, so a template's 32 columns x 8 phases are 256
+// consecutive floats of its cc_sum row.  The transpose swaps the two low phase bits of the lane with the
+// two low column bits of the register index: afterwards registers 4g..4g+3 of a lane are FOUR CONSECUTIVE
+// outputs (one 16-byte red.v4), the 8 lanes of a template cover one 128-byte run per g, and the lane
+// keeps its own template -- 8 vector reductions per chunk instead of 32 scalar ones.
+// base points at output 8*(first column of the chunk - q) + 8*(lane & 3) + 4*((lane >> 2) & 1) of the lane's
+// template, i0 is that output's index (valid iff lo <= i <= hi).
 // mode 2: everything valid; 1: per-element predicate; 0: nothing to write.
-__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, float *const (&base)[4],
-                                             const int (&i0)[4], const int (&lo)[4], const int (&hi)[4], int mode,
-                                             float ithr, float scale, bool b16, bool b8, uint64_t policy, int debug) {
+__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, float *base, int i0, int lo, int hi,
+                                             int mode, float ithr, float scale, bool b2, bool b1, uint64_t policy,
+                                             int debug) {
     float v[32];
     tc_ld32(taddr, v);
-    if (debug & 1) mode = (v[0] == 12345.678f) ? mode : 0;  // triage: keep everything but the reductions
+    if (debug & 1) mode = (v[0] == 12345.678f) ? mode : 0;  // triage: keep everything but the epilogue math + reductions
     if (mode == 0) return;
 #pragma unroll
     for (int c = 0; c < 32; c++) {
@@ -229,25 +245,32 @@ __device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, f
         v[c] = (w < ithr) ? x * scale : 0.f;
     }
 #pragma unroll
-    for (int g = 0; g < 8; g++) tc_transpose4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], b16, b8);
+    for (int g = 0; g < 8; g++) tc_transpose4<2, 1>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], b2, b1);
+    if (debug & 8) {  // triage: epilogue math without the global writes
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; c++) s += v[c];
+        if (s != 12345.678f) return;
+    }
     if (mode == 2 && (debug & 4)) {  // triage: plain stores instead of reductions (wrong results)
 #pragma unroll
         for (int g = 0; g < 8; g++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) base[x][32 * g] = v[4 * g + x];
+            *reinterpret_cast<float4 *>(base + 32 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     } else if (mode == 2) {
 #pragma unroll
-        for (int g = 0; g < 8; g++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) red_add_f32(base[x] + 32 * g, v[4 * g + x], policy);
+        for (int g = 0; g < 8; g++) red_add_v4(base + 32 * g, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], policy);
     } else {
 #pragma unroll
-        for (int g = 0; g < 8; g++)
+        for (int g = 0; g < 8; g++) {
+            const int i = i0 + 32 * g;
+            if (i >= lo && i + 3 <= hi) {
+                red_add_v4(base + 32 * g, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], policy);
+            } else {
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
-                const int i = i0[x] + 32 * g;
-                if (i >= lo[x] && i <= hi[x]) red_add_f32(base[x] + 32 * g, v[4 * g + x], policy);
+                for (int x = 0; x < 4; x++)
+                    if (i + x >= lo && i + x <= hi) red_add_f32(base + 32 * g + x, v[4 * g + x], policy);
             }
+        }
     }
 }
 
@@ -272,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
         mbar_init(a_empty, 1);
         for (int i = 0; i < 2; i++) {
             mbar_init(acc_full + i, 1);
-            mbar_init(acc_empty + i, 8);  // one arrive per epilogue warp
+            mbar_init(acc_empty + i, TC_EPI_WARPS);  // one arrive per epilogue warp
         }
         for (int i = 0; i < TC_NB; i++) {
             mbar_init(b_full + i, 1);
@@ -370,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 tc_commit(a_empty);  // A image may be replaced once every MMA of this item retired
             }
         }
-    } else if (warp == TC_EPI_WARP0 + 8) {
+    } else if (warp == TC_EPI_WARP0 + TC_EPI_WARPS) {
         // ===================== rsqrt(energy) producer: 32-column slices for the epilogue ===========
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
@@ -401,10 +424,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     } else {
         // ===================== epilogue: TMEM -> normalise -> red.add into cc_sum ==================
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
-        const int half = (warp - TC_EPI_WARP0) >> 2;       // which 128 columns of the tile
+        const int half = ((warp - TC_EPI_WARP0) >> 2) & 1; // which 128 columns of the tile
+        const int sub = (warp - TC_EPI_WARP0) >> 3;        // which chunks of that half: sub, sub + TC_EPI_SUBS, ...
         const int row = quarter * 32 + lane;               // A row == TMEM lane
         const uint64_t red_policy = l2_policy_evict_last();
-        uint32_t n_tile = 0, n_chunk = 0;
+        uint32_t n_tile = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const TcItem im = tc_decode(p, it);
             const int ch = im.ch, mt = im.mt, seg = im.seg;
@@ -426,20 +450,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 jj_lo = (long long)((a >= 0) ? (a + 7) / 8 : -((-a) / 8)) + q;  // ceil(a / 8) + q
                 jj_hi = (long long)((b >= 0) ? b / 8 : -((-b + 7) / 8)) + q;    // floor(b / 8) + q
             }
-            // the warp's four templates after the transpose: row base, column shift, valid range
-            float *tbase[4];
-            int tq[4], tlo[4], thi[4];
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                const int tx = mt * TC_TPL + quarter * 4 + x;
-                const size_t mr = (size_t)(ch * p.MT + mt) * TC_ROWS + quarter * 32 + 8 * x;
-                tq[x] = p.row_q[mr];
-                const bool live = tx < p.T && p.row_scale[mr] != 0.f;
-                tlo[x] = live ? p.lo[tx] : 1;
-                thi[x] = live ? p.hi[tx] : 0;
-                tbase[x] = p.cc + (size_t)(tx < p.T ? tx : 0) * p.cc_pitch + lane;
-            }
-            const bool b16 = (lane & 16) != 0, b8 = (lane & 8) != 0;
+            // after the transpose the lane still writes its own template: 16-byte pieces at
+            // 8 * (lane & 3) + 4 * ((lane >> 2) & 1) floats into each 128-byte run
+            float *obase = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + 8 * (lane & 3) + 4 * ((lane >> 2) & 1);
+            const bool b2 = (lane & 2) != 0, b1 = (lane & 1) != 0;
             const int t_begin = seg * p.seg_tiles;
             const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
             for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
@@ -455,20 +469,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 const int mode = __all_sync(0xffffffffu, c_lo == 0 && c_hi == 128)
                                      ? 2 : (__any_sync(0xffffffffu, c_hi > c_lo) ? 1 : 0);
 #pragma unroll 1
-                for (int chunk = 0; chunk < 4; chunk++, n_chunk++) {
+                for (int chunk = sub; chunk < 4; chunk += TC_EPI_SUBS) {
+                    const uint32_t n_chunk = 4 * n_tile + (uint32_t)chunk;  // chunks of this half issued so far
                     const int slot = n_chunk % TC_NI;
                     uint64_t *full = inv_full + half * TC_NI + slot;
                     mbar_wait(full, (n_chunk / TC_NI) & 1);
                     const float *inv = inv_s + (half * TC_NI + slot) * TC_INV_SLOT + e;
-                    float *cbase[4];
-                    int ci0[4];
-#pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        const long long o = 8 * (jj0 + chunk * 32 - tq[x]);  // output index of lane 0, register group 0
-                        cbase[x] = tbase[x] + o;
-                        ci0[x] = (int)(o + lane);
-                    }
-                    tc_epi_chunk(taddr + (uint32_t)(chunk * 32), inv, cbase, ci0, tlo, thi, mode, ithr, scale, b16, b8,
+                    const long long o = 8 * (jj0 + chunk * 32 - q);  // output index of column 0, phase 0
+                    tc_epi_chunk(taddr + (uint32_t)(chunk * 32), inv, obase + o,
+                                 (int)(o + 8 * (lane & 3) + 4 * ((lane >> 2) & 1)), lo, hi, mode, ithr, scale, b2, b1,
                                  red_policy, p.debug);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(inv_empty + half * TC_NI + slot);

@@ -272,7 +272,8 @@ def test_large_dynamic_range_traces():
     quiet windows: the fp16 operands are scaled per channel by a power of two of the channel maximum and
     stay in the normal range over ~9 decades.  Checked against the float64 brute force (window-local sums):
     a global float64 prefix sum -- what mf_oracle.c and upstream use -- loses ~1e-4 of the energy of
-    every window after a 3e7 spike, the block-local prefix sums of the CUDA pre-pass do not."""
+    every window after a 3e7 spike (and a block-local one still does inside the spike's block); the
+    segment-local sums of the CUDA pre-pass (mf_prepass.cu) never subtract, so they do not."""
     tp, mv, w, d, planted = _synth.mf_case(3, 3, 2, 200, 24000, seed=61, zero_gap=False)
     d = d.copy()
     d[:, :, 12000:12050] *= 1.0e5
@@ -282,8 +283,13 @@ def test_large_dynamic_range_traces():
         got = fmf.matched_filter(tp, mv, w, d, 1, precision=prec, check_zeros=False)
         assert np.isfinite(got).all()
         assert np.abs(got - want).max() < _tol(prec, 200, w), prec
-        for t, i0 in planted.items():
-            assert abs(got[t, i0] - w[t].sum()) < _tol(prec, 200, w) + 1e-6
+        n_clean = 0
+        for t, i0 in planted.items():  # planted windows that the transients do not overlap still peak at sum(w)
+            if abs(want[t, i0] - w[t].sum()) < 1e-6:
+                n_clean += 1
+                assert abs(got[t, i0] - w[t].sum()) < _tol(prec, 200, w) + 1e-6
+                assert int(got[t].argmax()) == i0
+        assert n_clean >= 2
     # raw counts (no normalisation, amplitudes ~1e6) and tiny physical units (~1e-3) give the same CC
     for gain in (1.0e6, 1.0e-3):
         got = fmf.matched_filter(tp * np.float32(gain), mv, w, d * np.float32(gain), 1, check_zeros=False)
