@@ -16,6 +16,13 @@
 //   reduce   : "max" keeps a running (max, argmax) per sample in registers and merges source
 //              chunks with a packed 64-bit atomicMax (value-ordered bits << 32 | ~k, so ties go to
 //              the lowest source index); "none" stores b[k,t].
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "async.cuh"
 #include "common.cuh"
 
 namespace bpmf {
@@ -269,6 +276,428 @@ __global__ void __launch_bounds__(B_THREADS, 2)
     }
 }
 
+// ---------------------------------------------------------------- grouped, warp-specialised beam kernel
+// The sources are cut into super-blocks of 16 consecutive sources; inside a super-block, consecutive
+// sources are grouped greedily as long as, for EVERY (station, phase) row, the moveouts of the group's
+// weighted members fit one staged window (spread <= F_MARGIN samples).  Neighbouring grid points
+// give groups of 16; unrelated moveouts degrade to groups of one source, never to a different code path.
+//   beam_pack_kernel : warp per super-block -> transposed moveouts tauT[sb][sp][16], weights
+//                      betaT[sb][s][16] and the group list grp[sb][16] (start | count << 8, 0 = end).
+//   beam_group_kernel: CTA = 768-sample time tile x a range of super-blocks.  One PRODUCER warp walks
+//                      (group, row): window start = min moveout of the group, (offset, weight) table of
+//                      the row, one cp.async.bulk (TMA) of the <= 5 KB row window into a ring of
+//                      F_NSTAGE stages, completion on the stage's "full" mbarrier.  Eight CONSUMER warps
+//                      (16 sources x 3 samples of register accumulators per thread, lanes = consecutive
+//                      samples: conflict-free 4-byte LDS per gather-FMA) wait on "full", accumulate,
+//                      and release the stage on its "empty" mbarrier -- no CTA-wide barrier, warps drift.
+constexpr int F_CONS_WARPS = 8;
+constexpr int F_CONS = 32 * F_CONS_WARPS;        // consumer threads
+constexpr int F_THREADS = F_CONS + 32;           // + the producer warp
+constexpr int F_R = 3;                           // samples per consumer thread: 16 x 3 accumulators leave room, inside the 96
+                                                 // registers that let two CTAs share an SM, for gathers in flight
+constexpr int F_TT = F_CONS * F_R;               // 768-sample tile
+constexpr int F_G = 16;                          // sources per super-block / largest group
+constexpr int F_MARGIN = 512;                    // largest moveout spread inside a group (samples)
+constexpr int F_WIN = F_TT + F_MARGIN;           // staged row window (floats)
+constexpr int F_NSTAGE = 8;
+constexpr int F_DIRECT_MAX = 2;                  // groups of up to two sources are gathered straight from global memory
+constexpr int F_STAGE = F_WIN + 2 * F_G + 8;     // + (offset, weight) table + header (skip flag), floats; x4 B is a multiple of 16
+
+__device__ __forceinline__ long long align4_down(long long v) { return v & ~3ll; }
+
+__global__ void __launch_bounds__(128)
+    beam_pack_kernel(const int *__restrict__ tau, const float *__restrict__ beta, size_t K, int S, int P,
+                     int *__restrict__ tauT, float *__restrict__ betaT, unsigned short *__restrict__ grp,
+                     int *__restrict__ dlist, int *__restrict__ dcount) {
+    extern __shared__ long long pack_sm[];  // per warp: mn[SP], mx[SP]
+    const int SP = S * P;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t sb = (size_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const size_t n_sb = (K + F_G - 1) / F_G;
+    if (sb >= n_sb) return;
+    long long *mn_s = pack_sm + (size_t)wib * 2 * SP, *mx_s = mn_s + SP;
+    const size_t k0 = sb * F_G;
+    const int nk = (int)((K - k0 < (size_t)F_G) ? (K - k0) : (size_t)F_G);
+    // transposes (reads are contiguous: 16 consecutive sources)
+    for (int e = lane; e < F_G * SP; e += 32) {
+        const int j = e / SP, sp = e - j * SP;
+        tauT[(sb * SP + sp) * F_G + j] = (j < nk) ? tau[(k0 + j) * SP + sp] : 0;
+    }
+    for (int e = lane; e < F_G * S; e += 32) {
+        const int j = e / S, s = e - j * S;
+        betaT[(sb * S + s) * F_G + j] = (j < nk) ? beta[(k0 + j) * S + s] : 0.f;
+    }
+    // greedy grouping
+    for (int sp = lane; sp < SP; sp += 32) { mn_s[sp] = LLONG_MAX; mx_s[sp] = LLONG_MIN; }
+    int g_count = 0, g_start = 0, g_n = 0;
+    for (int j = 0; j < nk; j++) {
+        bool bad = false;
+        for (int sp = lane; sp < SP; sp += 32) {
+            if (beta[(k0 + j) * S + sp / P] == 0.f) continue;
+            const long long v = tau[(k0 + j) * SP + sp];
+            const long long a = v < mn_s[sp] ? v : mn_s[sp], b = v > mx_s[sp] ? v : mx_s[sp];
+            if (b - align4_down(a) > F_MARGIN) bad = true;
+        }
+        if (__any_sync(0xffffffffu, bad)) {  // close the group, source j starts the next one
+            if (lane == 0) grp[sb * F_G + g_count] = (unsigned short)(g_start | (g_n << 8));
+            g_count++;
+            g_start = j;
+            g_n = 0;
+            for (int sp = lane; sp < SP; sp += 32) { mn_s[sp] = LLONG_MAX; mx_s[sp] = LLONG_MIN; }
+        }
+        for (int sp = lane; sp < SP; sp += 32) {
+            if (beta[(k0 + j) * S + sp / P] == 0.f) continue;
+            const long long v = tau[(k0 + j) * SP + sp];
+            if (v < mn_s[sp]) mn_s[sp] = v;
+            if (v > mx_s[sp]) mx_s[sp] = v;
+        }
+        g_n++;
+    }
+    if (lane == 0) {
+        if (g_n > 0) grp[sb * F_G + g_count++] = (unsigned short)(g_start | (g_n << 8));
+        for (int g = g_count; g < F_G; g++) grp[sb * F_G + g] = 0;
+        // sources of the groups too small for a staged window go to beam_direct_kernel
+        for (int g = 0; g < g_count; g++) {
+            const unsigned gd = grp[sb * F_G + g];
+            const int n = (int)(gd >> 8), j0 = (int)(gd & 0xffu);
+            if (n > F_DIRECT_MAX) continue;
+            const int pos = atomicAdd(dcount, n);
+            for (int i = 0; i < n; i++) dlist[pos + i] = (int)(k0 + j0 + i);
+        }
+    }
+}
+
+// Two CTAs of 9 warps per SM: the register file is split over the four SM sub-partitions (16 384 registers
+// each), a sub-partition then hosts up to five of the 18 warps, so a thread may hold 96 registers.
+//
+// Record stream producer -> consumers (one record per stage): a record is one (station, phase) row that at
+// least one member of the group uses -- rows nobody uses are never emitted -- and every group ends with a
+// terminator record.  Record kinds: F_ROW_DENSE (straight-line code over the 16 positions; positions without
+// weight point at a block of zeros with weight 0, so that fmaf(0, 0, acc) leaves acc untouched whatever the
+// row holds), F_ROW_SPARSE (at most half of the positions weighted: warp-uniform branches), F_END.
+// Groups of one or two sources (unrelated moveouts) are not worth a staged window: beam_pack_kernel lists
+// their sources and beam_direct_kernel gathers them straight from the L2-resident rows (4 B per gather-FMA
+// either way, without the per-row hand-shake); both kernels merge into the same (max, argmax) keys.
+constexpr int F_ROW_DENSE = 0, F_ROW_SPARSE = 2, F_END = 1;
+
+template <bool REDUCE_MAX>
+__global__ void __launch_bounds__(F_THREADS, 2)
+    beam_group_kernel(const float *__restrict__ U, const int *__restrict__ tauT, const float *__restrict__ betaT,
+                      const unsigned short *__restrict__ grp, const int *__restrict__ tlo,
+                      const int *__restrict__ thi, size_t K, int S, int P, long long N, long long pitch, int strict,
+                      size_t sb_chunk, unsigned long long *__restrict__ keys, float *__restrict__ beam) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int SP = S * P;
+    float *stages = reinterpret_cast<float *>(smem_raw);                        // F_NSTAGE x F_STAGE
+    float *zero_s = stages + F_NSTAGE * F_STAGE;                                // F_TT zeros
+    int *par_tau = reinterpret_cast<int *>(zero_s + F_TT);                      // 2 x SP x 16
+    float *par_beta = reinterpret_cast<float *>(par_tau + 2 * SP * F_G);        // 2 x S x 16
+    uint64_t *bars = reinterpret_cast<uint64_t *>(par_beta + 2 * S * F_G);
+    uint64_t *full = bars, *empty = bars + F_NSTAGE, *pfull = bars + 2 * F_NSTAGE;  // [F_NSTAGE], [F_NSTAGE], [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long t0 = (long long)blockIdx.x * F_TT;
+    const size_t n_sb = (K + F_G - 1) / F_G;
+    const size_t sb_begin = (size_t)blockIdx.y * sb_chunk;
+    const size_t sb_end = (sb_begin + sb_chunk < n_sb) ? sb_begin + sb_chunk : n_sb;
+
+    for (int i = tid; i < F_TT; i += F_THREADS) zero_s[i] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < F_NSTAGE; i++) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, F_CONS_WARPS);
+        }
+        mbar_init(pfull + 0, 1);
+        mbar_init(pfull + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == F_CONS_WARPS) {
+        // ===================== producer warp ==========================================================
+        const uint32_t par_bytes = (uint32_t)(sizeof(int) * SP * F_G + sizeof(float) * S * F_G);
+        uint32_t it = 0;
+        for (size_t sb = sb_begin; sb < sb_end; sb++) {
+            const uint32_t u = (uint32_t)(sb - sb_begin);
+            const int pb = u & 1;
+            __syncwarp();
+            if (lane == 0) {
+                if (u == 0) {
+                    mbar_expect_tx(pfull + pb, par_bytes);
+                    bulk_g2s(par_tau + pb * SP * F_G, tauT + sb * SP * F_G, (uint32_t)(sizeof(int) * SP * F_G), pfull + pb);
+                    bulk_g2s(par_beta + pb * S * F_G, betaT + sb * S * F_G, (uint32_t)(sizeof(float) * S * F_G), pfull + pb);
+                }
+                if (sb + 1 < sb_end) {  // the other buffer was last read for super-block sb - 1
+                    mbar_expect_tx(pfull + (pb ^ 1), par_bytes);
+                    bulk_g2s(par_tau + (pb ^ 1) * SP * F_G, tauT + (sb + 1) * SP * F_G,
+                             (uint32_t)(sizeof(int) * SP * F_G), pfull + (pb ^ 1));
+                    bulk_g2s(par_beta + (pb ^ 1) * S * F_G, betaT + (sb + 1) * S * F_G,
+                             (uint32_t)(sizeof(float) * S * F_G), pfull + (pb ^ 1));
+                }
+            }
+            mbar_wait(pfull + pb, (u >> 1) & 1);
+            const int *tau_p = par_tau + pb * SP * F_G;
+            const float *beta_p = par_beta + pb * S * F_G;
+            for (int g = 0; g < F_G; g++) {
+                const unsigned gd = grp[sb * F_G + g];
+                const int n = (int)(gd >> 8), j0 = (int)(gd & 0xffu);
+                if (n == 0) break;
+                if (n <= F_DIRECT_MAX) continue;  // left to beam_direct_kernel
+                for (int sp = 0; sp < SP; sp++) {
+                    const int s = sp / P;
+                    // lane a < 16 owns position a of the group (source slot j0 + a)
+                    float b = 0.f;
+                    int tv = 0;
+                    if (lane < n) {
+                        b = beta_p[s * F_G + j0 + lane];
+                        tv = tau_p[sp * F_G + j0 + lane];
+                    }
+                    const unsigned nz = __ballot_sync(0xffffffffu, b != 0.f);
+                    if (nz == 0u) continue;  // no member of the group uses this row: nothing is emitted
+                    int mn = (b != 0.f) ? tv : INT_MAX, mx = (b != 0.f) ? tv : INT_MIN;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) {  // lanes 16-31 hold the neutral elements
+                        const int x = __shfl_xor_sync(0xffffffffu, mn, o), y = __shfl_xor_sync(0xffffffffu, mx, o);
+                        mn = x < mn ? x : mn;
+                        mx = y > mx ? y : mx;
+                    }
+                    mn = __shfl_sync(0xffffffffu, mn, 0);
+                    mx = __shfl_sync(0xffffffffu, mx, 0);
+                    const int stage = it % F_NSTAGE;
+                    mbar_wait(empty + stage, ((it / F_NSTAGE) & 1) ^ 1);
+                    it++;
+                    float *st = stages + stage * F_STAGE;
+                    int *hdr = reinterpret_cast<int *>(st + F_WIN + 2 * F_G);
+                    const long long wlo = align4_down((long long)mn);
+                    const int dense = __popc(nz) > F_G / 2;
+                    if (lane < F_G)
+                        reinterpret_cast<int2 *>(st + F_WIN)[lane] =
+                            (b != 0.f) ? make_int2((int)((long long)tv - wlo), __float_as_int(b))
+                                       : make_int2((int)(zero_s - st), 0);
+                    if (lane == 0) hdr[0] = dense ? F_ROW_DENSE : F_ROW_SPARSE;
+                    // samples [g0, g0 + len) of the row are needed; the part outside [0, pitch) reads as zero
+                    const long long g0 = t0 + wlo;                                      // multiple of 4
+                    const int len = (int)(((long long)mx - wlo + F_TT + 3) & ~3ll);     // <= F_WIN
+                    long long a0 = g0 < 0 ? 0 : g0;
+                    long long b0 = (g0 + len < pitch) ? g0 + len : pitch;
+                    if (b0 < a0) a0 = b0 = g0 + len;
+                    const int za = (int)(a0 - g0), zb = (int)(b0 - g0);  // in-range part of the window: [za, zb)
+                    if (za > 0 || zb < len) {                            // edges of the record only
+                        for (int i = 4 * lane; i < len; i += 128)
+                            if (i < za || i >= zb) *reinterpret_cast<float4 *>(st + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (zb > za) {
+                            mbar_expect_tx(full + stage, (uint32_t)(zb - za) * 4u);
+                            bulk_g2s(st + za, U + (size_t)sp * pitch + a0, (uint32_t)(zb - za) * 4u, full + stage);
+                        } else {
+                            mbar_arrive(full + stage);
+                        }
+                    }
+                }
+                // terminator record of the group
+                const int stage = it % F_NSTAGE;
+                mbar_wait(empty + stage, ((it / F_NSTAGE) & 1) ^ 1);
+                it++;
+                if (lane == 0) {
+                    reinterpret_cast<int *>(stages + stage * F_STAGE + F_WIN + 2 * F_G)[0] = F_END;
+                    mbar_arrive(full + stage);
+                }
+            }
+        }
+    } else {
+        // ===================== consumer warps =========================================================
+        float best[F_R];
+        unsigned bestk[F_R];
+#pragma unroll
+        for (int r = 0; r < F_R; r++) { best[r] = -INFINITY; bestk[r] = 0u; }
+        uint32_t it = 0;
+        bool any = false;
+        for (size_t sb = sb_begin; sb < sb_end; sb++) {
+            for (int g = 0; g < F_G; g++) {
+                const unsigned gd = grp[sb * F_G + g];
+                const int n = (int)(gd >> 8), j0 = (int)(gd & 0xffu);
+                if (n == 0) break;
+                if (n <= F_DIRECT_MAX) continue;  // beam_direct_kernel gathers these straight from global memory
+                any = true;
+                float acc[F_G][F_R];
+#pragma unroll
+                for (int a = 0; a < F_G; a++)
+#pragma unroll
+                    for (int r = 0; r < F_R; r++) acc[a][r] = 0.f;
+                {
+                    for (;;) {
+                        const int stage = it % F_NSTAGE;
+                        mbar_wait(full + stage, (it / F_NSTAGE) & 1);
+                        it++;
+                        const float *st = stages + stage * F_STAGE;
+                        const int kind = reinterpret_cast<const int *>(st + F_WIN + 2 * F_G)[0];
+                        const int4 *pk4 = reinterpret_cast<const int4 *>(st + F_WIN);  // (offset, weight) of positions 2q, 2q + 1
+                        if (kind == F_ROW_DENSE) {
+#pragma unroll
+                            for (int q = 0; q < F_G / 2; q++) {
+                                const int4 v = pk4[q];
+                                const float b0 = __int_as_float(v.y), b1 = __int_as_float(v.w);
+                                const float *s0 = st + v.x + tid, *s1 = st + v.z + tid;
+#pragma unroll
+                                for (int r = 0; r < F_R; r++) acc[2 * q][r] = fmaf(b0, s0[F_CONS * r], acc[2 * q][r]);
+#pragma unroll
+                                for (int r = 0; r < F_R; r++) acc[2 * q + 1][r] = fmaf(b1, s1[F_CONS * r], acc[2 * q + 1][r]);
+                            }
+                        } else if (kind == F_ROW_SPARSE) {
+#pragma unroll
+                            for (int q = 0; q < F_G / 2; q++) {
+                                const int4 v = pk4[q];
+                                const float b0 = __int_as_float(v.y), b1 = __int_as_float(v.w);
+                                if (b0 != 0.f) {
+                                    const float *s0 = st + v.x + tid;
+#pragma unroll
+                                    for (int r = 0; r < F_R; r++) acc[2 * q][r] = fmaf(b0, s0[F_CONS * r], acc[2 * q][r]);
+                                }
+                                if (b1 != 0.f) {
+                                    const float *s1 = st + v.z + tid;
+#pragma unroll
+                                    for (int r = 0; r < F_R; r++) acc[2 * q + 1][r] = fmaf(b1, s1[F_CONS * r], acc[2 * q + 1][r]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty + stage);
+                        if (kind == F_END) break;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < F_G; a++) {
+                    if (a < n) {
+                        const size_t k = sb * F_G + j0 + a;
+                        long long lo_k = 0, hi_k = N - 1;
+                        if (strict) { lo_k = tlo[k]; hi_k = thi[k]; }
+#pragma unroll
+                        for (int r = 0; r < F_R; r++) {
+                            const long long t = t0 + tid + F_CONS * r;
+                            const float v = (t >= lo_k && t <= hi_k) ? acc[a][r] : 0.f;
+                            if (REDUCE_MAX) {
+                                if (v > best[r]) { best[r] = v; bestk[r] = (unsigned)k; }
+                            } else if (t < N) {
+                                beam[k * (size_t)N + (size_t)t] = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (REDUCE_MAX && any) {
+#pragma unroll
+            for (int r = 0; r < F_R; r++) {
+                const long long t = t0 + tid + F_CONS * r;
+                if (t < N) {
+                    const unsigned long long key =
+                        ((unsigned long long)ordered_bits(best[r]) << 32) | (unsigned long long)(~bestk[r]);
+                    atomicMax(keys + t, key);
+                }
+            }
+        }
+    }
+}
+
+// Sources whose moveouts are unrelated to their neighbours' (groups of one or two): no window is shared, so
+// nothing is staged -- every gather is a coalesced 128-byte read of the L2-resident row.  D_ROWS rows x D_R
+// samples of loads are in flight per thread; (station, phase) rows are added in the same order as in
+// beam_group_kernel, so both kernels give the same bits for the same source.
+constexpr int D_THREADS = 256, D_R = 4, D_TT = D_THREADS * D_R, D_KB = 4, D_ROWS = 4;
+
+template <bool REDUCE_MAX>
+__global__ void __launch_bounds__(D_THREADS)
+    beam_direct_kernel(const float *__restrict__ U, const int *__restrict__ tau, const float *__restrict__ beta,
+                       const int *__restrict__ dlist, const int *__restrict__ dcount, const int *__restrict__ tlo,
+                       const int *__restrict__ thi, int S, int P, long long N, long long pitch, int strict,
+                       unsigned long long *__restrict__ keys, float *__restrict__ beam) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int SP = S * P;
+    int *tau_s = reinterpret_cast<int *>(smem_raw);                 // D_KB x SP
+    float *beta_s = reinterpret_cast<float *>(tau_s + D_KB * SP);   // D_KB x S
+    int *k_s = reinterpret_cast<int *>(beta_s + D_KB * S);          // D_KB
+    const int n_d = *dcount;
+    const int tid = threadIdx.x;
+    const long long t0 = (long long)blockIdx.x * D_TT;
+    float best[D_R];
+    unsigned bestk[D_R];
+#pragma unroll
+    for (int r = 0; r < D_R; r++) { best[r] = -INFINITY; bestk[r] = 0u; }
+    bool any = false;
+    for (int i0 = blockIdx.y * D_KB; i0 < n_d; i0 += gridDim.y * D_KB) {
+        const int nk = (n_d - i0 < D_KB) ? (n_d - i0) : D_KB;
+        __syncthreads();
+        for (int e = tid; e < nk * SP; e += D_THREADS) {
+            const int kk = e / SP;
+            tau_s[e] = tau[(size_t)dlist[i0 + kk] * SP + (e - kk * SP)];
+        }
+        for (int e = tid; e < nk * S; e += D_THREADS) {
+            const int kk = e / S;
+            beta_s[e] = beta[(size_t)dlist[i0 + kk] * S + (e - kk * S)];
+        }
+        if (tid < nk) k_s[tid] = dlist[i0 + tid];
+        __syncthreads();
+        any = true;
+        for (int kk = 0; kk < nk; kk++) {
+            float acc[D_R];
+#pragma unroll
+            for (int r = 0; r < D_R; r++) acc[r] = 0.f;
+            for (int sp0 = 0; sp0 < SP; sp0 += D_ROWS) {
+                float x[D_ROWS][D_R], b[D_ROWS];
+#pragma unroll
+                for (int i = 0; i < D_ROWS; i++) {
+                    const int sp = sp0 + i;
+                    b[i] = (sp < SP) ? beta_s[kk * S + sp / P] : 0.f;
+                    const long long tv = (sp < SP) ? tau_s[kk * SP + sp] : 0;
+                    const float *row = U + (size_t)(sp < SP ? sp : 0) * pitch;
+#pragma unroll
+                    for (int r = 0; r < D_R; r++) {
+                        const long long gi = t0 + tid + D_THREADS * r + tv;
+                        x[i][r] = (b[i] != 0.f && gi >= 0 && gi < N) ? __ldg(row + gi) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < D_ROWS; i++)
+                    if (b[i] != 0.f) {
+#pragma unroll
+                        for (int r = 0; r < D_R; r++) acc[r] = fmaf(b[i], x[i][r], acc[r]);
+                    }
+            }
+            const int k = k_s[kk];
+            long long lo_k = 0, hi_k = N - 1;
+            if (strict) { lo_k = tlo[k]; hi_k = thi[k]; }
+#pragma unroll
+            for (int r = 0; r < D_R; r++) {
+                const long long t = t0 + tid + D_THREADS * r;
+                const float v = (t >= lo_k && t <= hi_k) ? acc[r] : 0.f;
+                if (REDUCE_MAX) {
+                    if (v > best[r] || (v == best[r] && (unsigned)k < bestk[r])) { best[r] = v; bestk[r] = (unsigned)k; }
+                } else if (t < N) {
+                    beam[(size_t)k * (size_t)N + (size_t)t] = v;
+                }
+            }
+        }
+    }
+    if (REDUCE_MAX && any) {
+#pragma unroll
+        for (int r = 0; r < D_R; r++) {
+            const long long t = t0 + tid + D_THREADS * r;
+            if (t < N) {
+                const unsigned long long key =
+                    ((unsigned long long)ordered_bits(best[r]) << 32) | (unsigned long long)(~bestk[r]);
+                atomicMax(keys + t, key);
+            }
+        }
+    }
+}
+
+static size_t beam_group_smem_bytes(size_t S, size_t P) {
+    return sizeof(float) * (F_NSTAGE * F_STAGE + F_TT) + 2 * (sizeof(int) * S * P * F_G + sizeof(float) * S * F_G) +
+           sizeof(uint64_t) * (2 * F_NSTAGE + 2);
+}
+
 __global__ void beam_finalize_kernel(const unsigned long long *__restrict__ keys, size_t N,
                                      int source_offset, float *__restrict__ maxbeam,
                                      int *__restrict__ argmax) {
@@ -302,6 +731,10 @@ struct BeamWs {
     float *U;
     int *tlo, *thi;
     unsigned long long *keys;
+    int *tauT;             // (n_sb, S*P, 16) transposed moveouts of the 16-source super-blocks
+    float *betaT;          // (n_sb, S, 16)
+    unsigned short *grp;   // (n_sb, 16) groups: start | count << 8, 0 terminates
+    int *dlist, *dcount;   // sources of the groups of <= F_DIRECT_MAX sources (any order), and how many
 };
 
 static BeamWs carve(Workspace &ws, size_t K, size_t S, size_t P, size_t N) {
@@ -310,6 +743,12 @@ static BeamWs carve(Workspace &ws, size_t K, size_t S, size_t P, size_t N) {
     b.tlo = ws.take<int>(K);
     b.thi = ws.take<int>(K);
     b.keys = ws.take<unsigned long long>(N);
+    const size_t n_sb = (K + F_G - 1) / F_G;
+    b.tauT = ws.take<int>(n_sb * S * P * F_G);
+    b.betaT = ws.take<float>(n_sb * S * F_G);
+    b.grp = ws.take<unsigned short>(n_sb * F_G);
+    b.dlist = ws.take<int>(K);
+    b.dcount = ws.take<int>(64);
     return b;
 }
 
@@ -336,7 +775,25 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
             d_tau, d_beta, K, (int)S, (int)P, (long long)N, b.tlo, b.thi);
         BPMF_LAUNCH_CHECK();
     }
-    const size_t n_tiles = (N + B_TT - 1) / B_TT;
+    // grouped warp-specialised kernel unless its shared-memory footprint rules out two CTAs per SM
+    // (hundreds of stations) or BPMF_BEAM_KERNEL=legacy asks for the barrier-synchronised one
+    const size_t gsmem = beam_group_smem_bytes(S, P);
+    bool grouped = gsmem <= 110 * 1024;
+    if (const char *e = getenv("BPMF_BEAM_KERNEL")) grouped = grouped && strcmp(e, "legacy") != 0;
+    const size_t n_sb = (K + F_G - 1) / F_G;
+    if (grouped && K > 0) {
+        const int warps = 4;
+        BPMF_CUDA(cudaMemsetAsync(b.dcount, 0, sizeof(int), st));
+        beam_pack_kernel<<<(unsigned)((n_sb + warps - 1) / warps), warps * 32,
+                           sizeof(long long) * 2 * S * P * warps, st>>>(d_tau, d_beta, K, (int)S, (int)P, b.tauT,
+                                                                         b.betaT, b.grp, b.dlist, b.dcount);
+        BPMF_LAUNCH_CHECK();
+    }
+    const size_t n_tiles = grouped ? (N + F_TT - 1) / F_TT : (N + B_TT - 1) / B_TT;
+    // direct kernel: its CTAs find the number of listed sources on the device and leave when there are none
+    const size_t d_tiles = (N + D_TT - 1) / D_TT;
+    const size_t dsmem = sizeof(int) * D_KB * (S * P + S + 1);
+    const dim3 dgrid((unsigned)d_tiles, (unsigned)std::max<size_t>(1, std::min<size_t>(64, (8 * (size_t)num_sms() + d_tiles - 1) / d_tiles)));
     if (reduce_max) {
         BPMF_CUDA(cudaMemsetAsync(b.keys, 0, sizeof(unsigned long long) * N, st));
         if (K > 0) {
@@ -344,19 +801,54 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
             // enough source chunks to fill the machine when the time axis is short
             const size_t want = (size_t)num_sms() * 4;
             size_t n_chunks = (n_tiles >= want) ? 1 : (want + n_tiles - 1) / n_tiles;
-            size_t k_chunk = align_up((K + n_chunks - 1) / n_chunks, B_KB);
-            n_chunks = (K + k_chunk - 1) / k_chunk;
-            BPMF_REQUIRE(n_chunks <= 65535, "beamform: too many source chunks");
-            BPMF_CUDA(cudaFuncSetAttribute(beam_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
-            beam_kernel<true><<<grid, B_THREADS, smem, st>>>(b.U, d_tau, d_beta, b.tlo, b.thi, K,
-                                                             (int)S, (int)P, (long long)N, (long long)pitch,
-                                                             flexible ? 0 : 1, k_chunk, b.keys, nullptr);
+            if (grouped) {
+                size_t sb_chunk = (n_sb + n_chunks - 1) / n_chunks;
+                n_chunks = (n_sb + sb_chunk - 1) / sb_chunk;
+                BPMF_REQUIRE(n_chunks <= 65535, "beamform: too many source chunks");
+                BPMF_CUDA(cudaFuncSetAttribute(beam_group_kernel<true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+                dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
+                beam_group_kernel<true><<<grid, F_THREADS, gsmem, st>>>(
+                    b.U, b.tauT, b.betaT, b.grp, b.tlo, b.thi, K, (int)S, (int)P, (long long)N, (long long)pitch,
+                    flexible ? 0 : 1, sb_chunk, b.keys, nullptr);
+                BPMF_LAUNCH_CHECK();
+                beam_direct_kernel<true><<<dgrid, D_THREADS, dsmem, st>>>(
+                    b.U, d_tau, d_beta, b.dlist, b.dcount, b.tlo, b.thi, (int)S, (int)P, (long long)N,
+                    (long long)pitch, flexible ? 0 : 1, b.keys, nullptr);
+            } else {
+                size_t k_chunk = align_up((K + n_chunks - 1) / n_chunks, B_KB);
+                n_chunks = (K + k_chunk - 1) / k_chunk;
+                BPMF_REQUIRE(n_chunks <= 65535, "beamform: too many source chunks");
+                BPMF_CUDA(cudaFuncSetAttribute(beam_kernel<true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
+                beam_kernel<true><<<grid, B_THREADS, smem, st>>>(b.U, d_tau, d_beta, b.tlo, b.thi, K,
+                                                                 (int)S, (int)P, (long long)N, (long long)pitch,
+                                                                 flexible ? 0 : 1, k_chunk, b.keys, nullptr);
+            }
             BPMF_LAUNCH_CHECK();
         }
         beam_finalize_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(b.keys, N, source_offset,
                                                                          d_max, d_arg);
+        BPMF_LAUNCH_CHECK();
+    } else if (K > 0 && grouped) {
+        size_t sb_chunk = 4;
+        size_t n_chunks = (n_sb + sb_chunk - 1) / sb_chunk;
+        if (n_chunks > 65535) {
+            sb_chunk = (n_sb + 65534) / 65535;
+            n_chunks = (n_sb + sb_chunk - 1) / sb_chunk;
+        }
+        BPMF_CUDA(cudaFuncSetAttribute(beam_group_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        MainKernelTimer timer(st);
+        dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
+        beam_group_kernel<false><<<grid, F_THREADS, gsmem, st>>>(
+            b.U, b.tauT, b.betaT, b.grp, b.tlo, b.thi, K, (int)S, (int)P, (long long)N, (long long)pitch,
+            flexible ? 0 : 1, sb_chunk, nullptr, d_beam);
+        BPMF_LAUNCH_CHECK();
+        beam_direct_kernel<false><<<dgrid, D_THREADS, dsmem, st>>>(
+            b.U, d_tau, d_beta, b.dlist, b.dcount, b.tlo, b.thi, (int)S, (int)P, (long long)N, (long long)pitch,
+            flexible ? 0 : 1, nullptr, d_beam);
         BPMF_LAUNCH_CHECK();
     } else if (K > 0) {
         size_t k_chunk = B_KB * 8;

@@ -85,3 +85,52 @@ def test_prestack():
     wp = np.random.default_rng(0).random(wp.shape).astype(np.float32)
     U = bp.prestack_traces(f, wp)
     assert np.abs(U - np.einsum("scp,scn->spn", wp, f)).max() < 1e-5
+
+
+def test_grouped_kernel_matches_legacy_kernel_bitwise(monkeypatch):
+    """The warp-specialised grouped kernel and the barrier-synchronised legacy kernel add the (station, phase)
+    rows of a source in the same order: identical bits, coherent (groups of 16) and random (groups of 1)."""
+    for coherent, sparse in ((True, False), (False, True), (True, True)):
+        f, tau, wp, ws = _synth.beam_case(333, 7, 2, 2, 6000, seed=11, sparse_sources=sparse, coherent=coherent)
+        monkeypatch.delenv("BPMF_BEAM_KERNEL", raising=False)
+        mb, am = bp.beamform(f, tau, wp, ws)
+        full = bp.beamform(f, tau, wp, ws, reduce="none")
+        monkeypatch.setenv("BPMF_BEAM_KERNEL", "legacy")
+        mb_l, am_l = bp.beamform(f, tau, wp, ws)
+        full_l = bp.beamform(f, tau, wp, ws, reduce="none")
+        monkeypatch.delenv("BPMF_BEAM_KERNEL", raising=False)
+        assert np.array_equal(mb, mb_l) and np.array_equal(am, am_l) and np.array_equal(full, full_l)
+
+
+@pytest.mark.parametrize("oob", ["strict", "flexible"])
+def test_negative_and_out_of_range_moveouts(oob):
+    """Moveouts below zero, beyond the end of the record, and a source whose every arrival is out of range."""
+    K, S, C, P, N = 70, 4, 2, 2, 5000
+    f, tau, wp, ws = _synth.beam_case(K, S, C, P, N, seed=21)
+    rng = np.random.default_rng(5)
+    tau = tau + rng.integers(-700, 300, size=(K, 1, 1))
+    tau[7] += 2 * N          # entirely beyond the record
+    tau[8, 1, :] = -3 * N    # one station far before the record
+    tau[40:44] += N - 600    # windows that straddle the end
+    mb, am = bp.beamform(f, tau, wp, ws, out_of_bounds=oob)
+    full = bp.beamform(f, tau, wp, ws, out_of_bounds=oob, reduce="none")
+    want = cpu.beamform(f, tau, wp, ws, out_of_bounds=oob, reduce="none")
+    assert np.abs(full - want).max() < 1e-5
+    assert np.array_equal(full.max(axis=0), mb) and np.array_equal(full.argmax(axis=0), am)
+
+
+def test_unused_station_garbage_is_ignored():
+    """NaN features and absurd moveouts on stations whose source weight is zero never reach the beam."""
+    K, S, C, P, N = 48, 6, 2, 2, 4000
+    f, tau, wp, ws = _synth.beam_case(K, S, C, P, N, seed=31, coherent=True)
+    ws[:, 2] = 0.0
+    ws[::3, 4] = 0.0
+    ws /= ws.sum(axis=1, keepdims=True)
+    want = cpu.beamform(f, tau, wp, ws, reduce="none")
+    f2, tau2 = f.copy(), tau.copy()
+    f2[2] = np.nan
+    tau2[:, 2, :] = 2 ** 30
+    tau2[::3, 4, :] = -(2 ** 30)
+    got = bp.beamform(f2, tau2, wp, ws, reduce="none")
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() < 1e-5
