@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(B_THREADS, 2)
                 const float *__restrict__ beta, const int *__restrict__ tlo,
                 const int *__restrict__ thi, size_t K, int S, int P, long long N, long long pitch, int strict,
                 size_t k_chunk, unsigned long long *__restrict__ keys, float *__restrict__ beam) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float *buf0 = reinterpret_cast<float *>(smem_raw);                 // B_NBUF x B_CAP (ring of row segments)
     int *tau_s = reinterpret_cast<int *>(buf0 + B_NBUF * B_CAP);       // B_KB * S * P
     float *beta_s = reinterpret_cast<float *>(tau_s + B_KB * S * P);   // B_KB * S
@@ -297,9 +297,15 @@ constexpr int F_R = 3;                           // samples per consumer thread:
                                                  // registers that let two CTAs share an SM, for gathers in flight
 constexpr int F_TT = F_CONS * F_R;               // 768-sample tile
 constexpr int F_G = 16;                          // sources per super-block / largest group
-constexpr int F_MARGIN = 512;                    // largest moveout spread inside a group (samples)
+#ifndef BEAM_MARGIN
+#define BEAM_MARGIN 512
+#endif
+#ifndef BEAM_NSTAGE
+#define BEAM_NSTAGE 8
+#endif
+constexpr int F_MARGIN = BEAM_MARGIN;                    // largest moveout spread inside a group (samples)
 constexpr int F_WIN = F_TT + F_MARGIN;           // staged row window (floats)
-constexpr int F_NSTAGE = 8;
+constexpr int F_NSTAGE = BEAM_NSTAGE;
 constexpr int F_DIRECT_MAX = 2;                  // groups of up to two sources are gathered straight from global memory
 constexpr int F_STAGE = F_WIN + 2 * F_G + 8;     // + (offset, weight) table + header (skip flag), floats; x4 B is a multiple of 16
 
@@ -613,7 +619,7 @@ __global__ void __launch_bounds__(D_THREADS)
                        const int *__restrict__ dlist, const int *__restrict__ dcount, const int *__restrict__ tlo,
                        const int *__restrict__ thi, int S, int P, long long N, long long pitch, int strict,
                        unsigned long long *__restrict__ keys, float *__restrict__ beam) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int SP = S * P;
     int *tau_s = reinterpret_cast<int *>(smem_raw);                 // D_KB x SP
     float *beta_s = reinterpret_cast<float *>(tau_s + D_KB * SP);   // D_KB x S
