@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-beam", action="store_true", help="skip the beamforming figure")
     ap.add_argument("--cpu-seconds", type=float, default=25.0)
     ap.add_argument("--batch", type=int, default=0, help="templates per kernel launch at N > 1 (0 = default)")
     return ap.parse_args()
@@ -376,6 +377,19 @@ def run_ours(args, rank, world, local_rank):
         except Exception as exc:  # noqa: BLE001 -- an extra figure must never break the contract line
             fused = {"error": str(exc)[:200]}
 
+    # ---- second hot path (extra object): beamforming / backprojection, BASELINE.json configs[2] scaled to a
+    # few seconds (the full 1e6-source x 1-day grid is ~1 minute per pass): source.samples/s and the
+    # shared-memory roofline fraction of SURVEY.md 8(d)
+    beam = None
+    if world == 1 and not args.no_beam:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_beam
+
+            beam = bench_beam.run(K=50000, N=432000, S=32, keep=32, steps=3, warmup=2, device_index=local_rank)
+        except Exception as exc:  # noqa: BLE001 -- an extra figure must never break the contract line
+            beam = {"error": str(exc)[:200]}
+
     # ---- end-to-end arm: the reference-facing call with pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -453,7 +467,7 @@ def run_ours(args, rank, world, local_rank):
                        (data.numel() * 4 + tp.numel() * 4) / 1e9, T * n_corr * 4 / 1e9),
                    "collective": collective},
         "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "parity": parity, "e2e_fused_detection": fused,
+        "parity": parity, "e2e_fused_detection": fused, "beamform": beam,
     }
     print(json.dumps(line))
 

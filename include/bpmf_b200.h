@@ -174,6 +174,24 @@ int bpmf_beamform_full_dev(const float *d_features, const int *d_moveouts,
 int bpmf_beam_merge_dev(float *d_max_a, int *d_arg_a, const float *d_max_b, const int *d_arg_b,
                         size_t n_samples, void *stream);
 
+/* ---------------------------------------------------------------- (2c) batched inter-template CC
+ * Replaces the loop of T fast_matched_filter calls (network_sum=False, zero moveouts, one template's
+ * waveforms as data) in TemplateGroup.compute_intertemplate_cc, BPMF/dataset.py:4784-4830:
+ *   cc[t, t2] = sum_{s,c} station_weights[t,s,c] * max over the 2*max_lag+1 lags of
+ *               CC( waveforms[t2,s,c, max_lag : n_samples-max_lag],  waveforms[t,s,c, lag : ...] )
+ * waveforms (T,S,C,n_samples) f32; station_weights (T,S,C) f32 (dataset.py:4806-4811, already normalised);
+ * pair_mask (T,T) bytes, 0 = pair not computed (cc = 0; dataset.py:4812-4814), NULL = all pairs; cc (T,T) f32,
+ * NOT symmetrised (the caller averages with the transpose, dataset.py:4833). */
+int bpmf_intertemplate_cc(const float *waveforms, const float *station_weights,
+                          const unsigned char *pair_mask, size_t n_templates, size_t n_stations,
+                          size_t n_components, size_t n_samples, size_t max_lag, float *cc);
+size_t bpmf_intertemplate_workspace_bytes(size_t n_templates, size_t n_stations, size_t n_components,
+                                          size_t max_lag);
+int bpmf_intertemplate_cc_dev(const float *d_waveforms, const float *d_station_weights,
+                              const unsigned char *d_pair_mask, size_t n_templates, size_t n_stations,
+                              size_t n_components, size_t n_samples, size_t max_lag, void *d_workspace,
+                              size_t workspace_bytes, float *d_cc, void *stream);
+
 /* ---------------------------------------------------------------- (1) BPMF/lib/libc.so symbols */
 /* libc.c:11-16   ; clib.py:26-33 */
 void kurtosis(float *signal, int W, int n_stations, int n_components, int length, float *kurto);

@@ -57,6 +57,9 @@ _SIGNATURES = {
     "bpmf_beamform_max_dev": (C.c_int, [vp, vp, vp, vp, z, z, z, z, z, C.c_int, C.c_int, vp, z, vp, vp, vp]),
     "bpmf_beamform_full_dev": (C.c_int, [vp, vp, vp, vp, z, z, z, z, z, C.c_int, vp, z, vp, vp]),
     "bpmf_beam_merge_dev": (C.c_int, [vp, vp, vp, vp, z, vp]),
+    "bpmf_intertemplate_cc": (C.c_int, [fp, fp, C.c_char_p, z, z, z, z, z, fp]),
+    "bpmf_intertemplate_workspace_bytes": (z, [z, z, z, z]),
+    "bpmf_intertemplate_cc_dev": (C.c_int, [vp, vp, vp, z, z, z, z, z, vp, z, vp, vp]),
     "kurtosis": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "find_similar_moveouts": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),
     "find_similar_moveouts2": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(F_THREADS, 2)
 
             // normalise + accumulate
             const float sst_v = sst[t * SC + ch];
+            const float sst_root = sqrtf(sst_v);
             const float sumt_v = FULL ? sumt[t * SC + ch] : 0.f;
             const float *ech = energy + (size_t)ch * n_win;
             const float *mch = FULL ? mean + (size_t)ch * n_win : nullptr;
@@ -126,8 +127,10 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                     const long long j = n + mv;
                     float num = acc[r];
                     if (FULL) num -= mch[j] * sumt_v;
-                    const float den = sst_v * ech[j];
-                    const float v = (den > MF_GUARD) ? num / sqrtf(den) : 0.f;
+                    // guard on the float64 product, quotient by the two roots: sst * E itself overflows
+                    // float32 for raw-count amplitudes (~1e13 transients)
+                    const float e_j = ech[j];
+                    const float v = ((double)sst_v * (double)e_j > (double)MF_GUARD) ? num / (sst_root * sqrtf(e_j)) : 0.f;
                     if (NETSUM)
                         total[r] = fmaf(w, v, total[r]);
                     else
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(F_THREADS)
                     acc[r] = fmaf(tk, d_s[(long long)(tid + F_THREADS * r) * step + k], acc[r]);
             }
             const float sst_v = sst[t * SC + ch];
+            const float sst_root = sqrtf(sst_v);
             const float sumt_v = FULL ? sumt[t * SC + ch] : 0.f;
             const float *ech = energy + (size_t)ch * n_win;
             const float *mch = FULL ? mean + (size_t)ch * n_win : nullptr;
@@ -204,8 +208,10 @@ __global__ void __launch_bounds__(F_THREADS)
                     const long long j = n * step + mv;
                     float num = acc[r];
                     if (FULL) num -= mch[j] * sumt_v;
-                    const float den = sst_v * ech[j];
-                    const float v = (den > MF_GUARD) ? num / sqrtf(den) : 0.f;
+                    // guard on the float64 product, quotient by the two roots: sst * E itself overflows
+                    // float32 for raw-count amplitudes (~1e13 transients)
+                    const float e_j = ech[j];
+                    const float v = ((double)sst_v * (double)e_j > (double)MF_GUARD) ? num / (sst_root * sqrtf(e_j)) : 0.f;
                     if (NETSUM)
                         total[r] = fmaf(w, v, total[r]);
                     else
