@@ -192,6 +192,20 @@ int bpmf_intertemplate_cc_dev(const float *d_waveforms, const float *d_station_w
                               size_t n_components, size_t n_samples, size_t max_lag, void *d_workspace,
                               size_t workspace_bytes, float *d_cc, void *stream);
 
+/* ---------------------------------------------------------------- (2d) travel times -> moveouts
+ * sec_to_samp (BPMF/utils.py:1257-1270): sign(t) * int64(|t * sampling_rate| + epsilon), evaluated in the dtype
+ * of the table (is_float64: 0 = float32, 1 = float64), then, if relative_to_first, minus the per-source minimum
+ * over (station, phase) (BPMF/template_search.py:212-219); moveout_to_tt[k] = that minimum / sampling_rate
+ * (may be NULL).  travel_times (K,S,P); moveouts (K,S,P) int32 -- the layout bpmf_beamform_* consume.  The
+ * device variant raises *d_overflow when a value does not fit int32 (the host variant returns BPMF_E_ARG). */
+int bpmf_moveouts_from_travel_times(const void *travel_times, int is_float64, size_t n_sources,
+                                    size_t n_stations, size_t n_phases, double sampling_rate, double epsilon,
+                                    int relative_to_first, int *moveouts, double *moveout_to_tt);
+int bpmf_moveouts_from_travel_times_dev(const void *d_travel_times, int is_float64, size_t n_sources,
+                                        size_t n_stations, size_t n_phases, double sampling_rate,
+                                        double epsilon, int relative_to_first, int *d_moveouts,
+                                        double *d_moveout_to_tt, int *d_overflow, void *stream);
+
 /* ---------------------------------------------------------------- (1) BPMF/lib/libc.so symbols */
 /* libc.c:11-16   ; clib.py:26-33 */
 void kurtosis(float *signal, int W, int n_stations, int n_components, int length, float *kurto);

@@ -60,6 +60,10 @@ _SIGNATURES = {
     "bpmf_intertemplate_cc": (C.c_int, [fp, fp, C.c_char_p, z, z, z, z, z, fp]),
     "bpmf_intertemplate_workspace_bytes": (z, [z, z, z, z]),
     "bpmf_intertemplate_cc_dev": (C.c_int, [vp, vp, vp, z, z, z, z, z, vp, z, vp, vp]),
+    "bpmf_moveouts_from_travel_times": (C.c_int, [vp, C.c_int, z, z, z, C.c_double, C.c_double, C.c_int, ip,
+                                                  C.POINTER(C.c_double)]),
+    "bpmf_moveouts_from_travel_times_dev": (C.c_int, [vp, C.c_int, z, z, z, C.c_double, C.c_double, C.c_int, vp, vp,
+                                                      vp, vp]),
     "kurtosis": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "find_similar_moveouts": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),
     "find_similar_moveouts2": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "csrc", "_obj")
 LIBNAME = "libbpmf_b200.so"
-SOURCES = ["abi.cu", "mf_prepass.cu", "mf_fp32.cu", "mf_tc.cu", "beam.cu", "libc_gpu.cu", "intertp.cu"]
+SOURCES = ["abi.cu", "mf_prepass.cu", "mf_fp32.cu", "mf_tc.cu", "beam.cu", "libc_gpu.cu", "intertp.cu", "moveouts.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -1,0 +1,101 @@
+"""Moveout tables for the beamformer.
+
+The reference rebuilds the ``(n_sources, n_stations, n_phases)`` moveout tensor with Python loops over stations x
+phases on EVERY access of ``Beamformer.moveouts`` (BPMF/template_search.py:444-454 -> ``TravelTimes.
+get_travel_times_array``, :170-219) -- once per ``backproject`` call and once per detection (:636) -- after
+converting seconds to samples column by column with ``utils.sec_to_samp`` (BPMF/utils.py:1257-1270).  Here the
+conversion is one CUDA pass (``bpmf_moveouts_from_travel_times``, include/bpmf_b200.h) and the result is cached:
+as an int32 tensor on the device for ``bpmf_beamform_*_dev`` and as a host array for callers that index it.
+There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def moveouts_from_travel_times(travel_times, sampling_rate, relative_to_first=True, epsilon=0.2):
+    """Seconds -> samples, bit-identical to the reference's ``sec_to_samp`` + ``relative_to_first``.
+
+    travel_times : (n_sources, n_stations, n_phases) float32 or float64 -- the dtype matters: the reference
+        evaluates ``|t * sr| + epsilon`` in the dtype of the table, and so does the kernel.
+    Returns ``(moveouts int32 (K, S, P), moveout_to_tt float64 (K,))``; ``moveout_to_tt`` is the per-source
+    first arrival in seconds (zeros when ``relative_to_first`` is False), template_search.py:212-219.
+    """
+    lib = _lib.load()
+    _lib.require_device()
+    tt = np.asarray(travel_times)
+    if tt.ndim != 3:
+        raise ValueError("expected travel_times (n_sources, n_stations, n_phases)")
+    if tt.dtype not in (np.float32, np.float64):
+        tt = tt.astype(np.float64)
+    tt = np.ascontiguousarray(tt)
+    K, S, P = tt.shape
+    mv = np.zeros((K, S, P), dtype=np.int32)
+    m2t = np.zeros(K, dtype=np.float64)
+    if tt.size:
+        rc = lib.bpmf_moveouts_from_travel_times(
+            tt.ctypes.data_as(C.c_void_p), 1 if tt.dtype == np.float64 else 0, K, S, P, float(sampling_rate),
+            float(epsilon), 1 if relative_to_first else 0, mv.ctypes.data_as(C.POINTER(C.c_int)),
+            m2t.ctypes.data_as(C.POINTER(C.c_double)))
+        _lib.check(rc, "bpmf_moveouts_from_travel_times")
+    return mv, m2t
+
+
+class MoveoutTable:
+    """Cached moveouts of a travel-time table, keyed like ``get_travel_times_array`` is called.
+
+    ``travel_times`` is ``{phase: {station: array(n_sources)}}`` (the layout of ``TravelTimes.travel_times``,
+    a pandas table of per-(station, phase) arrays, template_search.py:104-117) or a ``(K, S, P)`` array with
+    ``stations`` / ``phases`` naming its axes.  ``get(stations, phases)`` returns the same integers the
+    reference's property returns, computed once per key.
+    """
+
+    def __init__(self, travel_times, sampling_rate, stations=None, phases=None, relative_to_first=True):
+        self.sampling_rate = float(sampling_rate)
+        self.relative_to_first = bool(relative_to_first)
+        if isinstance(travel_times, np.ndarray):
+            if stations is None or phases is None or travel_times.shape[1:] != (len(stations), len(phases)):
+                raise ValueError("an array table needs matching `stations` and `phases` names")
+            self._cols = {(sta, ph): travel_times[:, s, p] for s, sta in enumerate(stations)
+                          for p, ph in enumerate(phases)}
+            self.stations, self.phases = list(stations), list(phases)
+        else:
+            self.phases = list(travel_times.keys()) if phases is None else list(phases)
+            first = travel_times[self.phases[0]]
+            self.stations = list(first.keys()) if stations is None else list(stations)
+            self._cols = {(sta, ph): np.asarray(travel_times[ph][sta]) for sta in self.stations for ph in self.phases}
+        self._cache = {}
+
+    def _key(self, stations, phases):
+        stations = self.stations if stations is None else list(stations)
+        phases = self.phases if phases is None else list(phases)
+        return tuple(stations), tuple(phases)
+
+    def get(self, stations=None, phases=None):
+        """(moveouts int32 (K, S, P), moveout_to_tt float64 (K,)) for the station / phase subset."""
+        key = self._key(stations, phases)
+        if key not in self._cache:
+            sta, ph = key
+            dtype = np.result_type(*[self._cols[(s, p)].dtype for s in sta for p in ph])
+            tt = np.stack([np.stack([self._cols[(s, p)] for p in ph], axis=-1) for s in sta], axis=1).astype(dtype)
+            self._cache[key] = moveouts_from_travel_times(tt, self.sampling_rate, self.relative_to_first)
+        return self._cache[key]
+
+    def moveouts(self, stations=None, phases=None):
+        return self.get(stations, phases)[0]
+
+    def moveout_to_tt(self, stations=None, phases=None):
+        return self.get(stations, phases)[1]
+
+    def device_moveouts(self, stations=None, phases=None, device=None):
+        """The cached table as a contiguous int32 CUDA tensor (what ``device.BeamformPlan`` takes)."""
+        import torch
+
+        key = ("dev",) + self._key(stations, phases) + (str(device),)
+        if key not in self._cache:
+            mv = self.moveouts(stations, phases)
+            dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+            self._cache[key] = torch.from_numpy(mv).to(dev)
+        return self._cache[key]
