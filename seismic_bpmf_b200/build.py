@@ -16,6 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "csrc", "_obj")
 LIBNAME = "libbpmf_b200.so"
+FEATURES_LIBNAME = "libbpmf_b200_features.so"  # detection traces (cuFFT + CUB); never loaded by the hot path
+FEATURES_SOURCES = ["features.cu"]
 SOURCES = ["abi.cu", "mf_prepass.cu", "mf_fp32.cu", "mf_tc.cu", "beam.cu", "libc_gpu.cu", "intertp.cu", "moveouts.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -37,6 +39,10 @@ def lib_path():
     return os.path.join(LIBDIR, LIBNAME)
 
 
+def features_lib_path():
+    return os.path.join(LIBDIR, FEATURES_LIBNAME)
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -49,9 +55,10 @@ def build(force=False, verbose=False):
     os.makedirs(OBJDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "bpmf_b200.h"))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "bpmf_b200_features.h"))
     nvcc = _nvcc()
     jobs = []
-    for src in SOURCES:
+    for src in SOURCES + FEATURES_SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
@@ -77,6 +84,13 @@ def build(force=False, verbose=False):
     out = lib_path()
     if force or jobs or _stale(out, objs):
         cmd = [nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    fobjs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in FEATURES_SOURCES]
+    fout = features_lib_path()
+    if force or jobs or _stale(fout, fobjs):
+        cmd = [nvcc, "-shared", "-o", fout] + fobjs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcufft"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -14,8 +14,8 @@ from seismic_bpmf_b200 import _lib, build
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "bpmf_b200.h")).read()
+def _declared_symbols(header="bpmf_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     text = re.sub(r"//[^\n]*", "", text)
     text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
@@ -32,6 +32,17 @@ def test_header_symbols_are_exported():
     assert not missing, "declared in include/bpmf_b200.h but not exported: %s" % missing
     # the ctypes table binds exactly the declared surface
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+
+
+def test_features_header_symbols_are_exported():
+    from seismic_bpmf_b200 import features
+
+    declared = _declared_symbols("bpmf_b200_features.h")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", build.features_lib_path()], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert not [n for n in declared if n not in exported]
+    assert sorted(features.EXPORTED_SYMBOLS) == declared
+    features.load()
 
 
 def test_reference_libc_symbol_set_is_covered():
