@@ -26,7 +26,7 @@ def test_oracle_matches_reference_vectors(golden):
     assert np.array_equal(f, golden["features_b"]) and np.array_equal(a, golden["availability_b"])
     assert list(golden["availability"]) == [2, 1, 2]  # the dead trace (MAD below the anomaly threshold) is dropped
     for tag in "abc":
-        window, overlap, cnr = golden["thr_%s_params" % tag]
+        window, overlap, cnr = (float(v) for v in golden["thr_%s_params" % tag])  # Python floats, as BPMF passes them
         thr = fo.time_dependent_threshold(golden["thr_%s_x" % tag], int(window), overlap=overlap, CNR_threshold=cnr)
         assert np.array_equal(thr, golden["thr_%s_out" % tag])
 
@@ -93,7 +93,7 @@ def test_backprojection_threshold_vs_reference_vectors(golden):
     from seismic_bpmf_b200 import features as ft
 
     for tag in "abc":
-        window, overlap, cnr = golden["thr_%s_params" % tag]
+        window, overlap, cnr = (float(v) for v in golden["thr_%s_params" % tag])  # Python floats, as BPMF passes them
         thr = ft.time_dependent_threshold(golden["thr_%s_x" % tag], int(window), overlap=overlap, CNR_threshold=cnr)
         want = golden["thr_%s_out" % tag]
         assert thr.dtype == np.float64 and thr.shape == want.shape
