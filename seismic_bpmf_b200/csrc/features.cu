@@ -71,7 +71,7 @@ __global__ void modulus_kernel(const cufftComplex *__restrict__ z, size_t N, flo
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const float a = z[i].x * inv_n, b = z[i].y * inv_n;
-    out[i] = sqrtf(a * a + b * b);
+    out[i] = hypotf(a, b);  // like np.abs(complex): no underflow of a*a for physical-unit amplitudes (~1e-20)
 }
 
 struct FftPlans {
@@ -101,7 +101,15 @@ static int envelope_rows(const float *d_traces, size_t rows, size_t N, cufftComp
     FEAT_CUFFT(cufftSetStream(g_plans.c2c, st));
     const unsigned blocks = (unsigned)((N + 255) / 256);
     for (size_t r = 0; r < rows; r++) {
-        FEAT_CUFFT(cufftExecR2C(g_plans.r2c, const_cast<float *>(d_traces + r * N), d_spec));
+        // cuFFT wants its real input aligned like a complex number: rows of odd length are staged in the
+        // full-spectrum buffer first (free until the R2C transform has produced `spec`)
+        const float *row = d_traces + r * N;
+        if (((uintptr_t)row & 15u) != 0) {
+            float *aligned = reinterpret_cast<float *>(d_full);
+            BPMF_CUDA(cudaMemcpyAsync(aligned, row, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+            row = aligned;
+        }
+        FEAT_CUFFT(cufftExecR2C(g_plans.r2c, const_cast<float *>(row), d_spec));
         analytic_spectrum_kernel<<<blocks, 256, 0, st>>>(d_spec, N, d_full);
         BPMF_LAUNCH_CHECK();
         FEAT_CUFFT(cufftExecC2C(g_plans.c2c, d_full, d_full, CUFFT_INVERSE));

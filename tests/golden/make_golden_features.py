@@ -37,7 +37,7 @@ def main():
     rng = np.random.default_rng(20240726)
     g = {}
     # traces: noise + transients, a gap, a mostly-missing trace, a dead (tiny MAD) trace, a huge spike (clipped)
-    S, C, N = 3, 2, 6001
+    S, C, N = 3, 2, 6075  # odd, 3^5 * 5^2: like BPMF's day-long records (86 400 s x 25/50/100 Hz) it has only small prime factors
     x = rng.standard_normal((S, C, N)).astype(np.float32) * np.float32(1e-6)
     x[0, 0, 2000:2100] *= 30.0
     x[0, 1, 1000:1500] = 0.0
