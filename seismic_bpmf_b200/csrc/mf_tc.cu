@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
         const int half = ((warp - TC_EPI_WARP0) >> 2) & 1; // which 128 columns of the tile
         const int sub = (warp - TC_EPI_WARP0) >> 3;        // which chunks of that half: sub, sub + TC_EPI_SUBS, ...
         const int row = quarter * 32 + lane;               // A row == TMEM lane
-        const uint64_t red_policy = l2_policy_evict_last();
+        const uint64_t red_policy = (p.debug & 32) ? l2_policy_evict_first() : l2_policy_evict_last();
         uint32_t n_tile = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const TcItem im = tc_decode(p, it);
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(TC_ROWS)
                             const float *__restrict__ ch_scale, int T, int SC, int L, int n_kc, int Kc, int split,
                             int a_bytes, int a_img_bytes, uint8_t *__restrict__ aimg, int *__restrict__ row_q,
                             int *__restrict__ row_e, float *__restrict__ row_scale, float *__restrict__ row_ithr,
-                            int *__restrict__ item_active) {
+                            int *__restrict__ item_active, int debug) {
     const int mt = blockIdx.x, ch = blockIdx.y, MT = gridDim.x;
     const int row = threadIdx.x;
     const int t = mt * TC_TPL + (row >> 3), ir = row & 7;
@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(TC_ROWS)
     // into ONE aligned 32-byte sector); the rest, e = ir + m mod 8 in [0, 15), is a delay of the row
     const int q0 = (m >= 0) ? (m >> 3) : -((-m + 7) >> 3);
     const int e = ir + (m - 8 * q0);
-    const int q = q0 + TC_FRONT / 8;  // staged traces start TC_FRONT samples early
+    int q = q0 + TC_FRONT / 8;  // staged traces start TC_FRONT samples early
+    if (debug & 16) q &= ~3;    // triage only (wrong results): every 128-byte reduction run is line-aligned
     const float *tp = templates + ((size_t)(t < T ? t : 0) * SC + ch) * (size_t)L;
     float sA = 1.f;
     if (used) {
@@ -623,6 +624,11 @@ static TcTplWs tc_carve_templates(Workspace &ws, const MfShape &sh, const TcGeom
     return w;
 }
 
+static int tc_debug_flags() {  // BPMF_TC_DEBUG: performance triage switches (see tc_epi_chunk), 0 in production
+    const char *dbg = getenv("BPMF_TC_DEBUG");
+    return dbg ? atoi(dbg) : 0;
+}
+
 bool mf_tc_supported(size_t L, size_t step, int normalize, int network_sum) {
     return step == 1 && normalize == 0 && network_sum != 0 && L >= 8 && L <= 65536;
 }
@@ -676,7 +682,7 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     tc_template_prep_kernel<<<dim3((unsigned)w.MT, (unsigned)SC), TC_ROWS, 0, st>>>(
         d_templates, d_moveouts, d_weights, meta.sst, meta.lo, meta.hi, tw.ch_scale, (int)sh.T, (int)SC, (int)sh.L,
         g.n_kc, g.Kc, split, g.a_bytes, g.a_img_bytes, w.aimg, w.row_q, w.row_e, w.row_scale, w.row_ithr,
-        w.item_active);
+        w.item_active, tc_debug_flags());
     BPMF_LAUNCH_CHECK();
     // cc_sum is accumulated with reductions: start from zero (also the value of never-computed outputs)
     BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * cc_pitch, st));
@@ -696,10 +702,7 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     p.seg_tiles = TC_SEG_TILES;
     if (const char *sg = getenv("BPMF_TC_SEG_TILES")) p.seg_tiles = std::max(1, atoi(sg));  // tuning experiments
     p.n_seg = (g.n_tiles + p.seg_tiles - 1) / p.seg_tiles;
-    {
-        const char *dbg = getenv("BPMF_TC_DEBUG");
-        p.debug = dbg ? atoi(dbg) : 0;
-    }
+    p.debug = tc_debug_flags();
     const long long n_items = (long long)p.n_seg * p.MT * p.SC * p.n_kc;
     BPMF_REQUIRE(n_items < (1ll << 31), "matched filter: too many work items for the tensor path");
     BPMF_CUDA(cudaFuncSetAttribute(mf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
