@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", help="skip the beamforming figure")
+    ap.add_argument("--callers", action="store_true",
+                    help="also time the SURVEY 8(f) rows (moveout tables, detection traces, inter-template CC) against "
+                         "their CPU restatements on bounded samples (adds ~1 min; off by default)")
     ap.add_argument("--cpu-seconds", type=float, default=25.0)
     ap.add_argument("--batch", type=int, default=0, help="templates per kernel launch at N > 1 (0 = default)")
     return ap.parse_args()
@@ -221,6 +224,75 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------ callers either side of the kernels
+def callers_figures():
+    """f2 / f3 / f4 through their public (reference-signature) entry points with HOST arrays, next to the CPU
+    restatement (oracle/, single process, the box's host cores as NumPy / SciPy use them) on the same inputs."""
+    from oracle import cpu, features_numpy as fo, moveouts_numpy as mo
+    from seismic_bpmf_b200 import features as ft, intertemplate as itp, template_search as ts
+
+    def timed(fn, reps=1):
+        fn()  # warm-up (cuFFT plans, allocations)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        return (time.perf_counter() - t0) / reps, out
+
+    rng = np.random.default_rng(SEED)
+    res = {}
+    # f2: travel-time table of 250 000 grid sources x 32 stations x 2 phases (float32 seconds) -> int32 moveouts
+    K, S, P = 250000, 32, 2
+    tt = rng.uniform(0.0, 60.0, (K, S, P)).astype(np.float32)
+    t_gpu, (mv, _) = timed(lambda: ts.moveouts_from_travel_times(tt, 50.0), 3)
+    t0 = time.perf_counter()
+    want, _ = mo.moveouts_from_travel_times(tt, 50.0)
+    t_cpu = time.perf_counter() - t0
+    res["moveouts"] = {"workload": "%d sources x %d stations x %d phases, float32 seconds -> samples, relative to first" % (K, S, P),
+                       "gpu_ms": 1e3 * t_gpu, "cpu_numpy_ms": 1e3 * t_cpu, "bit_exact": bool(np.array_equal(mv, want)),
+                       "h2d_bytes": int(tt.nbytes), "d2h_bytes": int(mv.nbytes)}
+    # f3: saturated envelopes of 8 stations x 3 components x 1 day @ 25 Hz, and the threshold of a 1-day max-beam
+    Sx, Cx, Nx = 8, 3, 2160000
+    traces = (rng.standard_normal((Sx, Cx, Nx)) * 1e-7).astype(np.float32)
+    traces[2, 1, 500000:700000] = 0.0
+    t_gpu, (feat, avail) = timed(lambda: ft.saturated_envelopes(traces), 2)
+    sub = traces[:1]  # the CPU restatement is timed on one station (3 traces) and scaled
+    t0 = time.perf_counter()
+    fw, aw = fo.saturated_envelopes(sub)
+    t_cpu = (time.perf_counter() - t0) * Sx
+    err = float(np.abs(feat[:1] - fw).max() / max(1.0, np.abs(fw).max()))
+    res["saturated_envelopes"] = {"workload": "%d stations x %d components x %d samples" % (Sx, Cx, Nx), "gpu_ms": 1e3 * t_gpu,
+                                  "cpu_scipy_ms_scaled_from_one_station": 1e3 * t_cpu, "max_rel_err_first_station": err,
+                                  "availability_matches": bool(np.array_equal(avail[:1], aw))}
+    nr = np.abs(rng.standard_normal(Nx)).astype(np.float32)
+    t_gpu, thr = timed(lambda: ft.time_dependent_threshold(nr, 45000, overlap=0.75, CNR_threshold=10.0), 2)
+    t0 = time.perf_counter()
+    thr_w = fo.time_dependent_threshold(nr, 45000, overlap=0.75, CNR_threshold=10.0)
+    t_cpu = time.perf_counter() - t0
+    res["bp_time_dependent_threshold"] = {"workload": "%d samples, 30 min windows @ 25 Hz, overlap 0.75" % Nx, "gpu_ms": 1e3 * t_gpu,
+                                          "cpu_scipy_ms": 1e3 * t_cpu,
+                                          "max_rel_err": float(np.abs(thr - thr_w).max() / np.abs(thr_w).max())}
+    # f4: inter-template CC of 400 templates x 10 stations x 3 components x 820 samples, max_lag 10
+    T, Sg, Cg, Lw, lag = 400, 10, 3, 820, 10
+    wav = rng.standard_normal((T, Sg, Cg, Lw)).astype(np.float32)
+    sw = np.full((T, Sg, Cg), 1.0 / (Sg * Cg), np.float32)
+    t_gpu, cc = timed(lambda: itp.intertemplate_cc(wav, sw, None, max_lag=lag), 3)
+    t_loop, cc_loop = timed(lambda: itp.intertemplate_cc_reference_loop(wav, sw, None, max_lag=lag), 1)
+    # one iteration of the reference's loop (dataset.py:4818-4830) with the CPU matched filter, scaled to T iterations
+    t0 = time.perf_counter()
+    cc1 = cpu.matched_filter(wav[..., lag: Lw - lag], np.zeros((T, Sg, Cg), np.int32), np.repeat(sw[:1], T, 0), wav[0], 1,
+                             network_sum=False, num_threads=os.cpu_count() or 1)
+    row0 = np.sum(sw[0] * np.max(cc1, axis=1), axis=(-1, -2))
+    t_cpu = (time.perf_counter() - t0) * T
+    cc_raw = itp.intertemplate_cc(wav, sw, None, max_lag=lag, symmetric=False)
+    res["intertemplate_cc"] = {"workload": "%d templates x %d stations x %d components x %d samples, max_lag %d (%.1e pair-channel-lags)"
+                               % (T, Sg, Cg, Lw, lag, T * T * Sg * Cg * (2 * lag + 1)),
+                               "gpu_batched_ms": 1e3 * t_gpu, "gpu_loop_of_matched_filter_calls_ms": 1e3 * t_loop,
+                               "cpu_oracle_loop_ms_scaled_from_one_iteration": 1e3 * t_cpu,
+                               "max_abs_diff_batched_vs_gpu_loop": float(np.abs(cc - cc_loop).max()),
+                               "max_abs_diff_row0_vs_cpu_oracle": float(np.abs(cc_raw[0] - row0).max())}
+    return res
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -390,6 +462,13 @@ def run_ours(args, rank, world, local_rank):
         except Exception as exc:  # noqa: BLE001 -- an extra figure must never break the contract line
             beam = {"error": str(exc)[:200]}
 
+    callers = None
+    if world == 1 and args.callers:
+        try:
+            callers = callers_figures()
+        except Exception as exc:  # noqa: BLE001
+            callers = {"error": str(exc)[:300]}
+
     # ---- end-to-end arm: the reference-facing call with pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -469,6 +548,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "parity": parity, "e2e_fused_detection": fused, "beamform": beam,
     }
+    if callers is not None:
+        line["callers"] = callers
     print(json.dumps(line))
 
 
