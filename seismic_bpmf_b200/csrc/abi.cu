@@ -7,6 +7,8 @@
 #include <mutex>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bpmf {
@@ -43,7 +45,11 @@ MainKernelTimer::~MainKernelTimer() {
 }
 
 static std::atomic<int> g_reserved_sms{0};
-int reserved_sms() { return g_reserved_sms.load(); }
+int reserved_sms() {
+    // BPMF_RESERVED_SMS overrides bpmf_set_reserved_sms() (tuning experiments: fewer SMs under the power cap)
+    if (const char *e = getenv("BPMF_RESERVED_SMS")) return atoi(e) < 0 ? 0 : atoi(e);
+    return g_reserved_sms.load();
+}
 
 int num_sms() {
     static int cached[64] = {0};
