@@ -134,3 +134,16 @@ def test_unused_station_garbage_is_ignored():
     got = bp.beamform(f2, tau2, wp, ws, reduce="none")
     assert np.isfinite(got).all()
     assert np.abs(got - want).max() < 1e-5
+
+
+@pytest.mark.parametrize("K,S,C,P,N", [(37, 40, 3, 3, 2500), (21, 200, 2, 2, 1800), (5, 1, 1, 1, 900)])
+def test_station_counts_beyond_one_warp_and_legacy_fallback(K, S, C, P, N):
+    """More (station, phase) rows than lanes (the pack kernel and the producer loop over them), and a network
+    large enough (200 stations x 2 phases) that the grouped kernel's parameter buffers no longer allow two CTAs per
+    SM: the barrier-synchronised kernel takes over.  Same answers either way."""
+    f, tau, wp, ws = _synth.beam_case(K, S, C, P, N, seed=K + S, coherent=True, sparse_sources=(S == 40))
+    mb, am = bp.beamform(f, tau, wp, ws)
+    full = bp.beamform(f, tau, wp, ws, reduce="none")
+    want = cpu.beamform(f, tau, wp, ws, reduce="none")
+    assert np.abs(full - want).max() < 2e-5 * max(1.0, float(np.abs(want).max()))
+    assert np.array_equal(full.max(axis=0), mb) and np.array_equal(full.argmax(axis=0), am)
