@@ -83,3 +83,43 @@ def beam_case(K, S, C, P, N, seed=SEED, tau_max=1500, sparse_sources=False, cohe
             ws[k, order[k, keep:]] = 0.0
     ws /= ws.sum(axis=1, keepdims=True)
     return feat, tau, wp, ws
+
+
+def day_case(S=8, K=343, N=60000, sr=50.0, n_events=3, seed=11):
+    """A miniature "day": S stations x 2 components (component 0 records the P phase, component 1 the S phase) of
+    unit-variance noise, a cubic grid of K sources under the network with P / S travel times (seconds), and
+    `n_events` distinct sources that each fire three times -- once strongly (8 sigma), twice weakly (2.5 sigma) --
+    with a source-and-channel specific 2 s wavelet.  Returns a dict with the traces, the travel-time table and the
+    ground truth (source, first-arrival sample of every occurrence)."""
+    rng = np.random.default_rng(seed)
+    n1 = int(round(K ** (1 / 3)))
+    K = n1 ** 3
+    g = np.stack(np.meshgrid(*(np.linspace(0.1, 0.9, n1),) * 3, indexing="ij"), -1).reshape(-1, 3)
+    g = g * np.array([60.0, 60.0, 20.0])
+    sta = np.concatenate([rng.uniform(0, 60, (S, 2)), np.zeros((S, 1))], axis=1)
+    dist = np.linalg.norm(g[:, None, :] - sta[None], axis=-1)
+    tt = np.stack([dist / 6.0, dist / 6.0 * 1.73], axis=-1).astype(np.float32)  # (K, S, 2) seconds
+    traces = rng.standard_normal((S, 2, N)).astype(np.float32)
+    wl = int(2 * sr)
+    taper = np.hanning(wl)
+    events = rng.choice(K, n_events, replace=False)
+    truth = []
+    samp = np.int64(np.sign(tt) * np.int64(np.abs(tt * np.float32(sr)) + np.float32(0.2)))  # utils.sec_to_samp
+    rel = samp - samp.min(axis=(1, 2), keepdims=True)
+    slots = rng.permutation(np.arange(3000, N - 8000, 4500))[: 3 * n_events]
+    for e, k in enumerate(events):
+        wav = rng.standard_normal((S, 2, wl)) * taper
+        wav /= np.sqrt((wav ** 2).mean(axis=-1, keepdims=True))
+        for r, amp in enumerate((8.0, 2.5, 2.5)):
+            i0 = int(slots[3 * e + r])
+            for s in range(S):
+                for c in range(2):
+                    j = i0 + int(rel[k, s, c])
+                    traces[s, c, j: j + wl] += (amp * wav[s, c]).astype(np.float32)
+            truth.append((int(k), i0, amp))
+    wp = np.zeros((S, 2, 2), dtype=np.float32)
+    wp[:, 0, 0] = 1.0
+    wp[:, 1, 1] = 1.0
+    ws = np.full((K, S), 1.0 / S, dtype=np.float32)
+    return dict(traces=traces, travel_times=tt, sr=sr, weights_phases=wp, weights_sources=ws, phase_on_comp=[0, 1],
+                truth=truth, grid=g)
