@@ -13,12 +13,36 @@ from types import SimpleNamespace
 import numpy as np
 
 
-def gpu_backend():
-    """The package's own (CUDA) entry points; raises when the libraries are missing -- no CPU fallback."""
+def _matched_filter_detect_dev(templates, moveouts, weights, data_arr, step, window, num_dev, overlap, search_win,
+                               white_noise):
+    """Matched filter + rms threshold + declustering with the CC slab kept on the device: only the
+    detections come back.  Same numbers as the per-template host calls it replaces."""
+    import torch
+
+    from . import device as dev
+
+    T, S, Cc, L = templates.shape
+    N = data_arr.shape[-1]
+    d = torch.device("cuda", torch.cuda.current_device())
+    plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, device=d)
+    up = [torch.from_numpy(np.ascontiguousarray(x)).to(d) for x in (
+        templates.astype(np.float32), moveouts.astype(np.int32), weights.astype(np.float32), data_arr.astype(np.float32))]
+    plan.run(*up)
+    s_, i_, _, _ = dev.detect_dev(plan.cc, torch.from_numpy(np.ascontiguousarray(white_noise, dtype=np.float32)).to(d),
+                                  num_dev, window // 2, int((1.0 - overlap) * window), search_win=search_win,
+                                  mode="select", n_valid=plan.n_corr, capacity=1 << 22)
+    return None, [i_[s_ == t].astype(np.int64) for t in range(T)]
+
+
+def gpu_backend(fused_detection=False):
+    """The package's own (CUDA) entry points; raises when the libraries are missing -- no CPU fallback.
+    ``fused_detection``: keep the CC slab on the device between the matched filter and the detection step."""
     from . import clib, fast_matched_filter as fmf, features, intertemplate, template_search
     from .beampower import beampower as bp
 
+    extra = {"matched_filter_detect": _matched_filter_detect_dev} if fused_detection else {}
     return SimpleNamespace(
+        **extra,
         saturated_envelopes=features.saturated_envelopes,
         bp_threshold=features.time_dependent_threshold,
         moveouts_from_travel_times=template_search.moveouts_from_travel_times,
@@ -83,12 +107,15 @@ def matched_filter_search(templates, template_moveouts, weights, data_arr, backe
                           search_win=None, white_noise=None, step=1):
     """CC time series of every template + rms threshold + declustering (similarity_search.py:526-533, 600-666).
     Returns ``(cc (T, n_corr), [detection indexes per template])``."""
-    cc = backend.matched_filter(templates, template_moveouts, weights, data_arr, step)
-    cc[np.isnan(cc)] = 0.0  # similarity_search.py:540
     if white_noise is None:
         white_noise = np.random.default_rng(0).standard_normal(500).astype(np.float32)
     if search_win is None:
         search_win = templates.shape[-1]
+    if hasattr(backend, "matched_filter_detect"):
+        return backend.matched_filter_detect(templates, template_moveouts, weights, data_arr, step, window, num_dev,
+                                             overlap, search_win, white_noise)
+    cc = backend.matched_filter(templates, template_moveouts, weights, data_arr, step)
+    cc[np.isnan(cc)] = 0.0  # similarity_search.py:540
     detections = []
     for t in range(cc.shape[0]):
         thr = backend.mf_threshold(cc[t], window, num_dev, overlap, white_noise)
@@ -110,7 +137,7 @@ def full_day(traces, travel_times, sampling_rate, weights_phases, weights_source
                                                template_offset, template_length)
     S, Cc = data_arr.shape[:2]
     weights = np.full((len(picks), S, Cc), 1.0 / (S * Cc), dtype=np.float32)
-    cc, detections = (np.zeros((0, 0), np.float32), [])
+    cc, detections = (None, [])
     intertp = np.zeros((0, 0), np.float32)
     if len(picks):
         cc, detections = matched_filter_search(templates, tmv, weights, data_arr, backend, mf_window, mf_num_dev)

@@ -112,3 +112,8 @@ def test_full_day_recovers_planted_events_and_matches_the_cpu_chain():
     assert np.abs(np.diag(itc) - 1.0).max() < 1e-5
     assert itc[same].min() > 0.5 and itc[~same].max() < 0.45
     assert np.abs(itc - ref.intertemplate_cc).max() < 1e-4
+    # the same day with the CC slab kept on the device between the matched filter and the detection step (f1)
+    fused = workflow.full_day(*args, backend=workflow.gpu_backend(fused_detection=True))
+    assert fused.cc is None and len(fused.detections) == len(gpu.detections)
+    for a, b in zip(fused.detections, gpu.detections):
+        assert np.array_equal(a, b)
