@@ -206,6 +206,14 @@ int bpmf_moveouts_from_travel_times_dev(const void *d_travel_times, int is_float
                                         double epsilon, int relative_to_first, int *d_moveouts,
                                         double *d_moveout_to_tt, int *d_overflow, void *stream);
 
+/* ---------------------------------------------------------------- (2e) trace normalisation
+ * MatchedFilter.set_data, BPMF/similarity_search.py:181-185: every one of the n_channels (station, component) traces
+ * is divided IN PLACE by its population standard deviation (0 -> 1); norm[n_channels] receives the divisors
+ * (self.data_norm).  Sums in float64.  The device variant needs 2 * n_channels doubles of scratch. */
+int bpmf_normalize_traces(float *data, size_t n_channels, size_t n_samples, float *norm);
+int bpmf_normalize_traces_dev(float *d_data, size_t n_channels, size_t n_samples, float *d_norm,
+                              double *d_scratch, void *stream);
+
 /* ---------------------------------------------------------------- (1) BPMF/lib/libc.so symbols */
 /* libc.c:11-16   ; clib.py:26-33 */
 void kurtosis(float *signal, int W, int n_stations, int n_components, int length, float *kurto);

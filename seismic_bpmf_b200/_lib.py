@@ -64,6 +64,8 @@ _SIGNATURES = {
                                                   C.POINTER(C.c_double)]),
     "bpmf_moveouts_from_travel_times_dev": (C.c_int, [vp, C.c_int, z, z, z, C.c_double, C.c_double, C.c_int, vp, vp,
                                                       vp, vp]),
+    "bpmf_normalize_traces": (C.c_int, [fp, z, z, fp]),
+    "bpmf_normalize_traces_dev": (C.c_int, [vp, z, z, vp, vp, vp]),
     "kurtosis": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "find_similar_moveouts": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),
     "find_similar_moveouts2": (None, [fp, fp, fp, fp, fp, C.c_float, z, z, z, z, z, C.c_int, ip]),

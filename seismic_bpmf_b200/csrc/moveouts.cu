@@ -10,6 +10,8 @@
 // (reads 4 or 8 bytes, writes 4 bytes per entry) whose int32 result stays on the device for bpmf_beamform_*_dev.
 #include <limits.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace bpmf {
@@ -106,5 +108,69 @@ extern "C" int bpmf_moveouts_from_travel_times(const void *travel_times, int is_
     BPMF_CUDA(cudaMemcpyAsync(&overflow, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     BPMF_CUDA(cudaStreamSynchronize(st));
     BPMF_REQUIRE(!overflow, "moveouts: a travel time does not fit 32-bit samples at %g Hz", sampling_rate);
+    return BPMF_OK;
+}
+
+// ---------------------------------------------------------------- trace normalisation
+// MatchedFilter.set_data, BPMF/similarity_search.py:181-185: every (station, component) trace is divided in place by
+// its standard deviation (population std, 0 -> 1) "to avoid problems with low numbers"; the norms are kept.
+// Three HBM-bound passes: mean, squared deviations (float64 sums, one CTA row per channel), then the scaling.
+namespace bpmf {
+// pass 0: sum of the channel; pass 1: sum of squared deviations from the mean of pass 0 (two passes: E[x^2] - mean^2
+// would lose the variance of a trace that rides on a large offset)
+__global__ void trace_moments_kernel(const float *__restrict__ data, size_t N, int pass, double *__restrict__ sums) {
+    const size_t ch = blockIdx.y;
+    const float *d = data + ch * N;
+    const double mean = pass ? sums[2 * ch] / (double)N : 0.0;
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = (double)d[i] - mean;
+        s += pass ? v * v : v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sums + 2 * ch + pass, s);
+}
+__global__ void trace_scale_kernel(float *__restrict__ data, size_t N, const double *__restrict__ sums,
+                                   float *__restrict__ norm) {
+    const size_t ch = blockIdx.y;
+    float sd = (float)sqrt(sums[2 * ch + 1] / (double)N);
+    if (sd == 0.f) sd = 1.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) norm[ch] = sd;
+    float *d = data + ch * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = __fdiv_rn(d[i], sd);
+}
+}  // namespace bpmf
+
+extern "C" int bpmf_normalize_traces_dev(float *d_data, size_t n_channels, size_t n_samples, float *d_norm,
+                                         double *d_scratch, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_channels == 0 || n_samples == 0) return BPMF_OK;
+    BPMF_REQUIRE(n_channels <= 65535, "normalize_traces: too many channels");
+    BPMF_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(double) * 2 * n_channels, st));
+    const dim3 grid((unsigned)std::min<size_t>(256, (n_samples + 1023) / 1024), (unsigned)n_channels);
+    trace_moments_kernel<<<grid, 256, 0, st>>>(d_data, n_samples, 0, d_scratch);
+    BPMF_LAUNCH_CHECK();
+    trace_moments_kernel<<<grid, 256, 0, st>>>(d_data, n_samples, 1, d_scratch);
+    BPMF_LAUNCH_CHECK();
+    trace_scale_kernel<<<grid, 256, 0, st>>>(d_data, n_samples, d_scratch, d_norm);
+    BPMF_LAUNCH_CHECK();
+    return BPMF_OK;
+}
+
+extern "C" int bpmf_normalize_traces(float *data, size_t n_channels, size_t n_samples, float *norm) {
+    if (n_channels == 0 || n_samples == 0) return BPMF_OK;
+    DevBuf d, nr, sc;
+    BPMF_CUDA(d.alloc(sizeof(float) * n_channels * n_samples));
+    BPMF_CUDA(nr.alloc(sizeof(float) * n_channels));
+    BPMF_CUDA(sc.alloc(sizeof(double) * 2 * n_channels));
+    cudaStream_t st = nullptr;
+    BPMF_CUDA(cudaMemcpyAsync(d.p, data, sizeof(float) * n_channels * n_samples, cudaMemcpyHostToDevice, st));
+    const int rc = bpmf_normalize_traces_dev(d.as<float>(), n_channels, n_samples, nr.as<float>(), sc.as<double>(), st);
+    if (rc != BPMF_OK) return rc;
+    BPMF_CUDA(cudaMemcpyAsync(data, d.p, sizeof(float) * n_channels * n_samples, cudaMemcpyDeviceToHost, st));
+    BPMF_CUDA(cudaMemcpyAsync(norm, nr.p, sizeof(float) * n_channels, cudaMemcpyDeviceToHost, st));
+    BPMF_CUDA(cudaStreamSynchronize(st));
     return BPMF_OK;
 }

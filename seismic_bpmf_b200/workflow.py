@@ -52,16 +52,34 @@ def gpu_backend(fused_detection=False):
             cc, win, num_dev, overlap=overlap, white_noise=noise),
         select_cc_indexes=clib.select_cc_indexes,
         intertemplate_cc=intertemplate.intertemplate_cc,
+        normalize_traces=normalize_traces,
     )
 
 
-def normalize_traces(data_arr):
-    """``MatchedFilter.set_data`` (similarity_search.py:181-185): divide every channel by its standard deviation
-    (0 -> 1) in place; returns the norms."""
+def normalize_traces_numpy(data_arr):
+    """The reference's own lines (similarity_search.py:181-185), for backends without a device."""
     norm = np.std(data_arr, axis=-1, keepdims=True)
     norm[norm == 0.0] = 1.0
     data_arr /= norm
     return norm.squeeze()
+
+
+def normalize_traces(data_arr):
+    """``MatchedFilter.set_data`` (similarity_search.py:181-185): divide every channel of the C-contiguous float32
+    ``(S, C, N)`` array by its standard deviation (0 -> 1) IN PLACE on the GPU; returns the norms ``(S, C)``."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    _lib.require_device()
+    assert data_arr.dtype == np.float32 and data_arr.flags.c_contiguous and data_arr.ndim == 3
+    S, Cc, N = data_arr.shape
+    norm = np.ones((S, Cc), dtype=np.float32)
+    fp = C.POINTER(C.c_float)
+    _lib.check(lib.bpmf_normalize_traces(data_arr.ctypes.data_as(fp), S * Cc, N, norm.ctypes.data_as(fp)),
+               "bpmf_normalize_traces")
+    return norm
 
 
 def backproject(traces, travel_times, sampling_rate, weights_phases, weights_sources, backend, window, overlap=0.75,
@@ -130,8 +148,8 @@ def full_day(traces, travel_times, sampling_rate, weights_phases, weights_source
     backend = gpu_backend() if backend is None else backend
     bp_res = backproject(traces, travel_times, sampling_rate, weights_phases, weights_sources, backend, bp_window,
                          cnr_threshold=bp_cnr)
-    data_arr = np.array(traces, dtype=np.float32, copy=True)
-    normalize_traces(data_arr)
+    data_arr = np.array(traces, dtype=np.float32, copy=True, order="C")
+    backend.normalize_traces(data_arr)
     picks, srcs = bp_res.picks, bp_res.sources[bp_res.picks]
     templates, tmv, origin = extract_templates(data_arr, bp_res.moveouts, phase_on_comp, picks, srcs,
                                                template_offset, template_length)

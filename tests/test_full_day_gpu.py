@@ -63,7 +63,8 @@ def _oracle_backend():
         saturated_envelopes=fo.saturated_envelopes, bp_threshold=fo.time_dependent_threshold,
         moveouts_from_travel_times=mv_from_tt, beamform=beamform,
         matched_filter=lambda tp, mv, w, d, step: cpu.matched_filter(tp, mv, w, d, step),
-        mf_threshold=mf_threshold, select_cc_indexes=_select_cc_indexes, intertemplate_cc=intertp)
+        mf_threshold=mf_threshold, select_cc_indexes=_select_cc_indexes, intertemplate_cc=intertp,
+        normalize_traces=workflow.normalize_traces_numpy)
 
 
 def test_full_day_recovers_planted_events_and_matches_the_cpu_chain():
@@ -117,3 +118,23 @@ def test_full_day_recovers_planted_events_and_matches_the_cpu_chain():
     assert fused.cc is None and len(fused.detections) == len(gpu.detections)
     for a, b in zip(fused.detections, gpu.detections):
         assert np.array_equal(a, b)
+
+
+def test_normalize_traces_matches_set_data():
+    """a5: in-place division by the per-channel standard deviation, 0 -> 1 (similarity_search.py:181-185)."""
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal((5, 3, 40001)) * rng.uniform(1e-6, 1e4, (5, 3, 1)) + rng.uniform(-3, 3, (5, 3, 1))).astype(np.float32)
+    x[2, 1] = 0.0
+    x[4, 0] = 7.5  # constant trace: zero variance
+    want = x.copy()
+    norm_w = workflow.normalize_traces_numpy(want)
+    got = x.copy()
+    norm_g = workflow.normalize_traces(got)
+    x64 = x.astype(np.float64)
+    std64 = x64.std(axis=-1)
+    std64[std64 == 0.0] = 1.0
+    assert np.abs(norm_g / std64 - 1.0).max() < 1e-6           # against float64 (NumPy's float32 std is the looser one)
+    assert np.abs(norm_g / norm_w - 1.0).max() < 1e-3
+    assert np.abs(got - x64 / std64[..., None]).max() < 1e-5 * np.abs(x64 / std64[..., None]).max()
+    assert norm_g[2, 1] == 1.0 and np.all(got[2, 1] == 0.0)
+    assert norm_g[4, 0] == 1.0 and np.all(got[4, 0] == np.float32(7.5))
