@@ -56,14 +56,6 @@ def gpu_backend(fused_detection=False):
     )
 
 
-def normalize_traces_numpy(data_arr):
-    """The reference's own lines (similarity_search.py:181-185), for backends without a device."""
-    norm = np.std(data_arr, axis=-1, keepdims=True)
-    norm[norm == 0.0] = 1.0
-    data_arr /= norm
-    return norm.squeeze()
-
-
 def normalize_traces(data_arr):
     """``MatchedFilter.set_data`` (similarity_search.py:181-185): divide every channel of the C-contiguous float32
     ``(S, C, N)`` array by its standard deviation (0 -> 1) IN PLACE on the GPU; returns the norms ``(S, C)``."""

@@ -14,6 +14,14 @@ from types import SimpleNamespace
 pytestmark = pytest.mark.gpu
 
 
+def _normalize_traces_numpy(data_arr):
+    """The reference's own lines, BPMF/similarity_search.py:181-185."""
+    norm = np.std(data_arr, axis=-1, keepdims=True)
+    norm[norm == 0.0] = 1.0
+    data_arr /= norm
+    return norm.squeeze()
+
+
 def _select_cc_indexes(cc, threshold, search_win):
     """libc.c:441-485, the sequential scan of oracle/libc_numpy.select_cc_indexes with the inner loop vectorised
     (same visiting order, same early exit): usable on day-long series."""
@@ -64,7 +72,7 @@ def _oracle_backend():
         moveouts_from_travel_times=mv_from_tt, beamform=beamform,
         matched_filter=lambda tp, mv, w, d, step: cpu.matched_filter(tp, mv, w, d, step),
         mf_threshold=mf_threshold, select_cc_indexes=_select_cc_indexes, intertemplate_cc=intertp,
-        normalize_traces=workflow.normalize_traces_numpy)
+        normalize_traces=_normalize_traces_numpy)
 
 
 def test_full_day_recovers_planted_events_and_matches_the_cpu_chain():
@@ -127,7 +135,7 @@ def test_normalize_traces_matches_set_data():
     x[2, 1] = 0.0
     x[4, 0] = 7.5  # constant trace: zero variance
     want = x.copy()
-    norm_w = workflow.normalize_traces_numpy(want)
+    norm_w = _normalize_traces_numpy(want)
     got = x.copy()
     norm_g = workflow.normalize_traces(got)
     x64 = x.astype(np.float64)
