@@ -11,7 +11,6 @@ from seismic_bpmf_b200 import workflow
 from tests import _synth
 from types import SimpleNamespace
 
-pytestmark = pytest.mark.gpu
 
 
 def _normalize_traces_numpy(data_arr):
@@ -75,6 +74,7 @@ def _oracle_backend():
         normalize_traces=_normalize_traces_numpy)
 
 
+@pytest.mark.gpu
 def test_full_day_recovers_planted_events_and_matches_the_cpu_chain():
     case = _synth.day_case()
     args = (case["traces"], case["travel_times"], case["sr"], case["weights_phases"], case["weights_sources"],
@@ -128,6 +128,7 @@ def test_full_day_recovers_planted_events_and_matches_the_cpu_chain():
         assert np.array_equal(a, b)
 
 
+@pytest.mark.gpu
 def test_normalize_traces_matches_set_data():
     """a5: in-place division by the per-channel standard deviation, 0 -> 1 (similarity_search.py:181-185)."""
     rng = np.random.default_rng(2)
