@@ -147,3 +147,18 @@ def test_normalize_traces_matches_set_data():
     assert np.abs(got - x64 / std64[..., None]).max() < 1e-5 * np.abs(x64 / std64[..., None]).max()
     assert norm_g[2, 1] == 1.0 and np.all(got[2, 1] == 0.0)
     assert norm_g[4, 0] == 1.0 and np.all(got[4, 0] == np.float32(7.5))
+
+
+def test_cpu_chain_alone_recovers_the_planted_events():
+    """The orchestration itself (host logic of workflow.py), driven with the CPU restatements only: no device."""
+    case = _synth.day_case()
+    res = workflow.full_day(case["traces"], case["travel_times"], case["sr"], case["weights_phases"],
+                            case["weights_sources"], case["phase_on_comp"], backend=_oracle_backend())
+    truth = case["truth"]
+    picked = {(k, i0) for p in res.backprojection.picks for k, i0, amp in truth if 20 <= int(p) - i0 <= 80}
+    assert {(k, i0) for k, i0, amp in truth if amp > 5} <= picked
+    for pick, dets in zip(res.origin, res.detections):
+        k = next(k for k, i0, amp in truth if 20 <= int(pick) - i0 <= 80)
+        lag = next(int(pick) - i0 for kk, i0, amp in truth if kk == k and 20 <= int(pick) - i0 <= 80)
+        assert sorted(int(d) for d in dets) == sorted(i0 + lag for kk, i0, amp in truth if kk == k)
+    assert np.abs(np.diag(res.intertemplate_cc) - 1.0).max() < 1e-5
