@@ -43,6 +43,12 @@ extern "C" {
 #define BPMF_MF_TC_FP16X3 3  /* tcgen05, hi/lo split of both operands (3 MMAs), fp32-grade */
 
 const char *bpmf_last_error(void);
+/* The reference-named symbols of group (1) return void (BPMF/libc.h:1-11) and can only report a
+ * failure on stderr.  bpmf_last_status() returns the code (0 or BPMF_E_*) of the calling thread's
+ * last such call, so that a binding can raise; on failure the float outputs (threshold, kurtosis)
+ * are additionally filled with NaN -- `cc > NaN` is false, so a caller that cannot check does not
+ * mistake a failed threshold for "everything is a detection". */
+int bpmf_last_status(void);
 int bpmf_device_count(void);
 /* library build id, e.g. "bpmf_b200 r1 sm_100a" */
 const char *bpmf_version(void);
@@ -84,7 +90,10 @@ int bpmf_matched_filter(const float *templates, const int *moveouts, const float
 /* Device-pointer entry point: every pointer is device memory, work is enqueued on `stream`
  * (a cudaStream_t passed as void*), no host synchronisation for an explicit precision.  `workspace` must hold at least
  * bpmf_mf_workspace_bytes(...) bytes.  cc_pitch = elements between consecutive template rows of
- * d_cc (>= n_corr; ignored when network_sum == 0). */
+ * d_cc (>= n_corr; ignored when network_sum == 0).  The tensor-core arithmetics (BPMF_MF_TC_*, and
+ * BPMF_MF_AUTO whenever the shape allows them) accumulate with vector reductions: d_cc must be
+ * 16-byte aligned and cc_pitch a multiple of 4 elements, otherwise the call returns BPMF_E_ARG
+ * (the Python wrappers pad rows to 64 elements). */
 size_t bpmf_mf_workspace_bytes(size_t n_samples_template, size_t n_samples_data,
                                size_t n_templates, size_t n_stations, size_t n_components,
                                size_t step, int normalize, int network_sum, int precision);

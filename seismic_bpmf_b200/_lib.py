@@ -29,6 +29,7 @@ vp = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
     "bpmf_last_error": (C.c_char_p, []),
+    "bpmf_last_status": (C.c_int, []),
     "bpmf_version": (C.c_char_p, []),
     "bpmf_device_count": (C.c_int, []),
     "bpmf_launch_count": (C.c_ulonglong, []),
@@ -108,6 +109,11 @@ def check(rc, what):
     if rc != OK:
         msg = load().bpmf_last_error()
         raise BpmfError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def check_void(what):
+    """After a reference-named (void) symbol: raise if the calling thread's last such call failed."""
+    check(load().bpmf_last_status(), what)
 
 
 def require_device():

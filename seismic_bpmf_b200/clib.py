@@ -27,6 +27,7 @@ def kurtosis(signal, W):
     signal = np.float32(signal.flatten())
     _libc.kurtosis(signal.ctypes.data_as(_fp), int(W), int(n_stations), int(n_components),
                    int(length), kurto.ctypes.data_as(_fp))
+    _lib.check_void("kurtosis")
     return kurto.reshape(n_stations, n_components, length)
 
 
@@ -56,6 +57,7 @@ def find_similar_sources(moveouts, source_longitude, source_latitude, cell_longi
        cell_latitude.ctypes.data_as(_fp), np.float32(threshold), int(n_sources), int(n_stations),
        int(n_cells_longitude), int(n_cells_latitude), int(num_stations_for_diff), int(num_threads),
        redundant_sources.ctypes.data_as(_ip))
+    _lib.check_void("find_similar_moveouts")
     return redundant_sources.astype(bool)
 
 
@@ -70,6 +72,7 @@ def select_cc_indexes(ccs, threshold, search_win):
     selection = np.zeros(n_corr, dtype=np.int32)
     _libc.select_cc_indexes(ccs.ctypes.data_as(_fp), threshold.ctypes.data_as(_fp), int(search_win),
                             int(n_corr), selection.ctypes.data_as(_ip))
+    _lib.check_void("select_cc_indexes")
     return selection.astype(bool)
 
 
@@ -91,4 +94,5 @@ def time_dependent_threshold(time_series, sliding_window_samp, num_dev, overlap=
     _libc.time_dependent_threshold(time_series.ctypes.data_as(_fp), white_noise.ctypes.data_as(_fp),
                                    float(num_dev), int(num_samples), int(half_window_samp),
                                    int(shift_samp), int(num_threads), threshold.ctypes.data_as(_fp))
+    _lib.check_void("time_dependent_threshold")
     return threshold

@@ -23,6 +23,9 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static thread_local int g_status = 0;
+void set_status(int rc) { g_status = rc; }
+
 static std::atomic<int> g_timing{0};
 constexpr int TIMER_RING = 256;
 static thread_local cudaEvent_t g_ev[TIMER_RING][2];
@@ -119,6 +122,7 @@ __global__ void mf_weight_norm_kernel(const float *__restrict__ w, size_t T, siz
 }
 
 static thread_local int g_last_precision = 0;
+static bool is_tc(int prec) { return prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3; }
 
 // AUTO on a tensor-capable shape: single-pass fp16 operands carry 2^-11 relative rounding; the CC
 // sum then errs by about 4e-4 * sqrt(sum_ch w^2) / sqrt(L) rms.  Take the single pass when 6.5
@@ -141,6 +145,7 @@ static int mf_auto_precision(const MfShape &sh, const float *d_weights, float *d
 using namespace bpmf;
 
 extern "C" const char *bpmf_last_error(void) { return g_err; }
+extern "C" int bpmf_last_status(void) { return g_status; }
 extern "C" const char *bpmf_version(void) { return "bpmf_b200 r1 sm_100a"; }
 extern "C" unsigned long long bpmf_launch_count(void) { return g_launches.load(); }
 
@@ -203,7 +208,6 @@ extern "C" int bpmf_mf_resolve_precision(size_t L, size_t step, int normalize, i
     return resolve_precision(sh, precision);
 }
 
-static bool is_tc(int prec) { return prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3; }
 // the split arithmetic needs the residual (lo) traces; AUTO may pick it at run time
 static bool wants_lo(int precision) { return precision == BPMF_MF_TC_FP16X3 || precision == BPMF_MF_AUTO; }
 
@@ -273,6 +277,10 @@ extern "C" int bpmf_mf_run_dev(const float *d_templates, const int *d_moveouts, 
     BPMF_REQUIRE(prec > 0, "matched_filter: precision %d is not available for L=%zu step=%zu "
                  "normalize=%d network_sum=%d", precision, L, step, normalize, network_sum);
     BPMF_REQUIRE(d_trace_ws && d_template_ws, "matched_filter: workspace missing");
+    // the tensor path accumulates with 8/16-byte vector reductions: rows of d_cc must start 16-byte aligned
+    BPMF_REQUIRE(!is_tc(prec) || ((cc_pitch & 3) == 0 && ((uintptr_t)d_cc & 15) == 0),
+                 "matched_filter: the tensor path needs d_cc 16-byte aligned and cc_pitch a multiple of 4 "
+                 "(got %p, %zu); pad the pitch (e.g. to 64 elements) or ask for BPMF_MF_FP32", (void *)d_cc, cc_pitch);
     Workspace tws(d_trace_ws, trace_ws_bytes), pws(d_template_ws, template_ws_bytes);
     float *scratch = pws.take<float>(64);
     MfMeta meta = carve_meta(pws, sh);
@@ -505,9 +513,10 @@ extern "C" void matched_filter(float *templates, float *sum_square_templates, in
                                size_t S, size_t C, size_t n_corr, int normalize, float *cc_sum) {
     (void)sum_square_templates;
     (void)n_corr;
-    if (bpmf_matched_filter(templates, moveouts, weights, data, step, L, N, T, S, C, normalize, 1,
-                            BPMF_MF_AUTO, cc_sum) != BPMF_OK)
-        fprintf(stderr, "libbpmf_b200: matched_filter failed: %s\n", bpmf_last_error());
+    const int rc = bpmf_matched_filter(templates, moveouts, weights, data, step, L, N, T, S, C, normalize, 1,
+                                       BPMF_MF_AUTO, cc_sum);
+    set_status(rc);
+    if (rc != BPMF_OK) fprintf(stderr, "libbpmf_b200: matched_filter failed: %s\n", bpmf_last_error());
 }
 
 extern "C" void matched_filter_no_sum(float *templates, float *sum_square_templates, int *moveouts,
@@ -516,7 +525,8 @@ extern "C" void matched_filter_no_sum(float *templates, float *sum_square_templa
                                       float *cc) {
     (void)sum_square_templates;
     (void)n_corr;
-    if (bpmf_matched_filter(templates, moveouts, weights, data, step, L, N, T, S, C, normalize, 0,
-                            BPMF_MF_AUTO, cc) != BPMF_OK)
-        fprintf(stderr, "libbpmf_b200: matched_filter_no_sum failed: %s\n", bpmf_last_error());
+    const int rc = bpmf_matched_filter(templates, moveouts, weights, data, step, L, N, T, S, C, normalize, 0,
+                                       BPMF_MF_AUTO, cc);
+    set_status(rc);
+    if (rc != BPMF_OK) fprintf(stderr, "libbpmf_b200: matched_filter_no_sum failed: %s\n", bpmf_last_error());
 }

@@ -11,6 +11,7 @@ namespace bpmf {
 
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char *fmt, ...);
+void set_status(int rc);  // outcome of the calling thread's last void-ABI call (bpmf_last_status)
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

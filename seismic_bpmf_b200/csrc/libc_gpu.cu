@@ -327,9 +327,13 @@ extern "C" void time_dependent_threshold(float *time_series, float *gaussian_sam
                                          size_t num_samples, size_t half_window_samp,
                                          size_t shift_samp, int num_threads, float *threshold) {
     (void)num_threads;
-    if (thr_host(time_series, gaussian_sample, num_dev, num_samples, half_window_samp, shift_samp,
-                 threshold) != BPMF_OK)
+    const int rc = thr_host(time_series, gaussian_sample, num_dev, num_samples, half_window_samp, shift_samp,
+                            threshold);
+    set_status(rc);
+    if (rc != BPMF_OK) {
         fprintf(stderr, "libbpmf_b200: time_dependent_threshold failed: %s\n", bpmf_last_error());
+        for (size_t i = 0; i < num_samples; i++) threshold[i] = NAN;  // `cc > NaN` is false: no false detections
+    }
 }
 
 // ================================================================ select_cc_indexes
@@ -372,8 +376,9 @@ static int select_host(float *cc, float *thr, size_t W, size_t n, int *sel) {
 
 extern "C" void select_cc_indexes(float *cc, float *threshold, size_t search_win, size_t n_corr,
                                   int *selection) {
-    if (select_host(cc, threshold, search_win, n_corr, selection) != BPMF_OK)
-        fprintf(stderr, "libbpmf_b200: select_cc_indexes failed: %s\n", bpmf_last_error());
+    const int rc = select_host(cc, threshold, search_win, n_corr, selection);
+    set_status(rc);
+    if (rc != BPMF_OK) fprintf(stderr, "libbpmf_b200: select_cc_indexes failed: %s\n", bpmf_last_error());
 }
 
 // ================================================================ kurtosis
@@ -434,8 +439,14 @@ static int kurtosis_host(float *signal, int W, int S, int C, int length, float *
 }
 
 extern "C" void kurtosis(float *signal, int W, int n_stations, int n_components, int length, float *kurto) {
-    if (kurtosis_host(signal, W, n_stations, n_components, length, kurto) != BPMF_OK)
+    const int rc = kurtosis_host(signal, W, n_stations, n_components, length, kurto);
+    set_status(rc);
+    if (rc != BPMF_OK) {
         fprintf(stderr, "libbpmf_b200: kurtosis failed: %s\n", bpmf_last_error());
+        const size_t n = (size_t)(n_stations > 0 ? n_stations : 0) * (size_t)(n_components > 0 ? n_components : 0) *
+                         (size_t)(length > 0 ? length : 0);
+        for (size_t i = 0; i < n; i++) kurto[i] = NAN;
+    }
 }
 
 // ================================================================ find_similar_moveouts[2]
@@ -621,18 +632,20 @@ extern "C" void find_similar_moveouts(float *moveouts, float *lon, float *lat, f
                                       float *cell_lat, float threshold, size_t K, size_t S, size_t n_cl,
                                       size_t n_ct, size_t n_for_diff, int num_threads, int *redundant) {
     (void)num_threads;
-    if (fsm_host(1, moveouts, lon, lat, cell_lon, cell_lat, threshold, K, S, n_cl, n_ct, n_for_diff,
-                 redundant) != BPMF_OK)
-        fprintf(stderr, "libbpmf_b200: find_similar_moveouts failed: %s\n", bpmf_last_error());
+    const int rc = fsm_host(1, moveouts, lon, lat, cell_lon, cell_lat, threshold, K, S, n_cl, n_ct, n_for_diff,
+                            redundant);
+    set_status(rc);
+    if (rc != BPMF_OK) fprintf(stderr, "libbpmf_b200: find_similar_moveouts failed: %s\n", bpmf_last_error());
 }
 
 extern "C" void find_similar_moveouts2(float *moveouts, float *lon, float *lat, float *cell_lon,
                                        float *cell_lat, float threshold, size_t K, size_t S, size_t n_cl,
                                        size_t n_ct, size_t n_for_diff, int num_threads, int *redundant) {
     (void)num_threads;
-    if (fsm_host(2, moveouts, lon, lat, cell_lon, cell_lat, threshold, K, S, n_cl, n_ct, n_for_diff,
-                 redundant) != BPMF_OK)
-        fprintf(stderr, "libbpmf_b200: find_similar_moveouts2 failed: %s\n", bpmf_last_error());
+    const int rc = fsm_host(2, moveouts, lon, lat, cell_lon, cell_lat, threshold, K, S, n_cl, n_ct, n_for_diff,
+                            redundant);
+    set_status(rc);
+    if (rc != BPMF_OK) fprintf(stderr, "libbpmf_b200: find_similar_moveouts2 failed: %s\n", bpmf_last_error());
 }
 
 // ================================================================ helper symbols (libc.h:5-10)

@@ -78,6 +78,25 @@ struct TcParams {
     int debug;  // BPMF_TC_DEBUG bit 0: skip the reductions (perf triage only)
 };
 
+// A row (= TMEM lane) <-> (template of the tile, phase).
+//   EPI 0: row = 8 * template + phase.  The epilogue reads one row per thread (tcgen05.ld.32x32b) and
+//          transposes 4 x 4 blocks with warp shuffles to form 16-byte reductions.
+//   EPI 1: within a quarter of 32 lanes, lane = 16*h + 8*v + 4*a + p holds template 4*quarter + 2*h + a,
+//          phase 2*p + v: lanes l and l + 8 of a 16-lane half are the two phases of a pair.  tcgen05.ld.16x128b
+//          hands thread t rows t/4 and t/4 + 8 of the half -- two CONSECUTIVE outputs of one template -- at
+//          columns (t & 3) + 4k: no shuffle, one 8-byte red.v2 per column, and the 16 threads of a template
+//          cover 4 columns x 8 phases = one 128-byte run per warp instruction.
+__host__ __device__ __forceinline__ void tc_row_decode(int row, int epi, int &tpl, int &phase) {
+    if (epi == 0) {
+        tpl = row >> 3;
+        phase = row & 7;
+    } else {
+        const int lam = row & 31;
+        tpl = 4 * (row >> 5) + 2 * (lam >> 4) + ((lam >> 2) & 1);
+        phase = 2 * (lam & 3) + ((lam >> 3) & 1);
+    }
+}
+
 struct TcItem {
     int kc, ch, mt, seg;
 };
@@ -171,6 +190,64 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
                  : "memory");
 }
 
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b, uint64_t policy) {
+    asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(a), "f"(b), "l"(policy)
+                 : "memory");
+}
+// 16 lanes x 32 columns: thread t gets rows t/4 (even registers) and t/4 + 8 (odd registers) of the 16-lane
+// group at columns (t & 3) + 4k, k = register / 2.  No wait: the caller issues tcgen05.wait::ld.
+__device__ __forceinline__ void tc_ld16x128_x8(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x128b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// per-thread constants of one template-phase pair of the shuffle-free epilogue (EPI 1)
+struct TcPair {
+    float scale, ithr;
+    float *obase;   // cc row of the template + ioff_out
+    int q, ioff;    // whole-column shift; 8 * (lane & 3) + delay of phase 2p (index into the rsqrt slice)
+    int ioff_out;   // 8 * (lane & 3) + 2p: the thread's first output relative to (column 0 of the chunk, phase 0)
+    int lo, hi;     // valid output range of the template
+    int jj_full_lo, jj_full_hi;  // columns where BOTH phases are valid
+    int jj_any_lo, jj_any_hi;    // columns where at least one is
+};
+
+__device__ __forceinline__ int floor_div8(int a) { return a >> 3; }          // arithmetic shift = floor
+__device__ __forceinline__ int ceil_div8(int a) { return (a + 7) >> 3; }
+
+// one 16-lane half of a 32-column chunk: 8 columns x 2 phases per thread
+__device__ __forceinline__ void tc_epi_half2(const uint32_t (&r)[16], const float *inv, const TcPair &pr, long long o,
+                                             int mode, uint64_t policy) {
+    // o = output index of (column 0 of the chunk, phase 0) for this template
+    const float *iv = inv + pr.ioff;
+    float *base = pr.obase + o;
+    if (mode == 2) {
+        if (pr.hi < pr.lo) return;  // unweighted template of a tile whose other templates are fully valid
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float w0 = iv[32 * k], w1 = iv[32 * k + 1];
+            const float x0 = __uint_as_float(r[2 * k]) * w0, x1 = __uint_as_float(r[2 * k + 1]) * w1;
+            red_add_v2(base + 32 * k, (w0 < pr.ithr) ? x0 * pr.scale : 0.f, (w1 < pr.ithr) ? x1 * pr.scale : 0.f,
+                       policy);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float w0 = iv[32 * k], w1 = iv[32 * k + 1];
+            const float x0 = __uint_as_float(r[2 * k]) * w0, x1 = __uint_as_float(r[2 * k + 1]) * w1;
+            const float y0 = (w0 < pr.ithr) ? x0 * pr.scale : 0.f, y1 = (w1 < pr.ithr) ? x1 * pr.scale : 0.f;
+            const long long i = o + pr.ioff_out + 32 * k;
+            if (i >= pr.lo && i <= pr.hi) red_add_f32(base + 32 * k, y0, policy);
+            if (i + 1 >= pr.lo && i + 1 <= pr.hi) red_add_f32(base + 32 * k + 1, y1, policy);
+        }
+    }
+}
+
 // one 32-column chunk of the epilogue: TMEM -> registers -> normalise -> transpose -> red.global.add.
 // inv points at this row's first rsqrt(energy) value of the chunk (column c lives 8*c floats on).
 // Lane (a, r) [a = lane >> 3: template of the warp, r = lane & 7: phase] holds columns c = 0..31 of its
@@ -226,6 +303,7 @@ __device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float *inv, f
 }
 
 // ---------------------------------------------------------------- the kernel
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a_s = smem;
@@ -372,6 +450,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 }
             }
         }
+    } else if (EPI == 1) {
+        // ===================== epilogue, shuffle-free: 16x128b TMEM loads -> normalise -> red.v2 ==========
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+        const int half = ((warp - TC_EPI_WARP0) >> 2) & 1; // which 128 columns of the tile
+        const int sub = (warp - TC_EPI_WARP0) >> 3;        // which chunks of that half: sub, sub + TC_EPI_SUBS, ...
+        const uint64_t red_policy = l2_policy_evict_last();
+        const int pp = (lane >> 2) & 3;                    // phase pair of this thread: phases 2pp, 2pp + 1
+        uint32_t n_tile = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const TcItem im = tc_decode(p, it);
+            const int ch = im.ch, mt = im.mt, seg = im.seg;
+            if (!p.item_active[ch * p.MT + mt]) continue;
+            TcPair pr[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                // row of phase 2pp of this thread's template in 16-lane half hh (lam = 16 hh + 4 a + pp)
+                const int row0 = quarter * 32 + 16 * hh + 4 * (lane >> 4) + pp;
+                const size_t mrow = (size_t)(ch * p.MT + mt) * TC_ROWS + row0;
+                const int t = mt * TC_TPL + 4 * quarter + 2 * hh + (lane >> 4);
+                TcPair &r = pr[hh];
+                r.scale = p.row_scale[mrow];
+                r.ithr = p.row_ithr[mrow];
+                r.q = p.row_q[mrow];
+                r.ioff = 8 * (lane & 3) + p.row_e[mrow];
+                r.ioff_out = 8 * (lane & 3) + 2 * pp;
+                r.lo = 1;
+                r.hi = 0;
+                if (t < p.T && r.scale != 0.f) { r.lo = p.lo[t]; r.hi = p.hi[t]; }
+                r.obase = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + r.ioff_out;
+                r.jj_full_lo = r.jj_any_lo = 1;
+                r.jj_full_hi = r.jj_any_hi = 0;
+                if (r.hi >= r.lo) {  // output of (column jj, phase ph) = 8 * (jj - q) + ph
+                    r.jj_full_lo = ceil_div8(r.lo - 2 * pp) + r.q;
+                    r.jj_full_hi = floor_div8(r.hi - 2 * pp - 1) + r.q;
+                    r.jj_any_lo = ceil_div8(r.lo - 2 * pp - 1) + r.q;
+                    r.jj_any_hi = floor_div8(r.hi - 2 * pp) + r.q;
+                }
+            }
+            const int t_begin = seg * p.seg_tiles;
+            const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+            for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
+                const int s = n_tile & 1;
+                mbar_wait(acc_full + s, (n_tile >> 1) & 1);
+                tc_fence_after();
+                const int jj0 = tile * TC_NCOL + half * 128;  // first column of this half
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_NCOL + half * 128);
+                int mode[2];
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const bool full = (pr[hh].hi < pr[hh].lo) || (pr[hh].jj_full_lo <= jj0 && pr[hh].jj_full_hi >= jj0 + 127);
+                    const bool any = pr[hh].jj_any_lo <= jj0 + 127 && pr[hh].jj_any_hi >= jj0;
+                    mode[hh] = !__any_sync(0xffffffffu, any) ? 0 : (__all_sync(0xffffffffu, full) ? 2 : 1);
+                }
+                if (p.debug & 1) mode[0] = mode[1] = 0;  // triage: MMA + producers only
+#pragma unroll 1
+                for (int chunk = sub; chunk < 4; chunk += TC_EPI_SUBS) {
+                    const uint32_t n_chunk = 4 * n_tile + (uint32_t)chunk;  // chunks of this half issued so far
+                    const int slot = n_chunk % TC_NI;
+                    uint64_t *full = inv_full + half * TC_NI + slot;
+                    uint32_t r0[16], r1[16];
+                    tc_ld16x128_x8(taddr + (uint32_t)(chunk * 32), r0);
+                    tc_ld16x128_x8(taddr + (16u << 16) + (uint32_t)(chunk * 32), r1);
+                    mbar_wait(full, (n_chunk / TC_NI) & 1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float *inv = inv_s + (half * TC_NI + slot) * TC_INV_SLOT;
+                    if (mode[0]) tc_epi_half2(r0, inv, pr[0], 8ll * (jj0 + chunk * 32 - pr[0].q), mode[0], red_policy);
+                    if (mode[1]) tc_epi_half2(r1, inv, pr[1], 8ll * (jj0 + chunk * 32 - pr[1].q), mode[1], red_policy);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(inv_empty + half * TC_NI + slot);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + s);
+            }
+        }
     } else {
         // ===================== epilogue: TMEM -> normalise -> red.add into cc_sum ==================
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
@@ -502,10 +655,12 @@ __global__ void __launch_bounds__(TC_ROWS)
                             const float *__restrict__ ch_scale, int T, int SC, int L, int n_kc, int Kc, int split,
                             int a_bytes, int a_img_bytes, uint8_t *__restrict__ aimg, int *__restrict__ row_q,
                             int *__restrict__ row_e, float *__restrict__ row_scale, float *__restrict__ row_ithr,
-                            int *__restrict__ item_active, int debug) {
+                            int *__restrict__ item_active, int debug, int epi) {
     const int mt = blockIdx.x, ch = blockIdx.y, MT = gridDim.x;
     const int row = threadIdx.x;
-    const int t = mt * TC_TPL + (row >> 3), ir = row & 7;
+    int tl, ir;
+    tc_row_decode(row, epi, tl, ir);
+    const int t = mt * TC_TPL + tl;
     const size_t item = (size_t)ch * MT + mt;
     const size_t mrow = item * TC_ROWS + row;
 
@@ -629,6 +784,11 @@ static int tc_debug_flags() {  // BPMF_TC_DEBUG: performance triage switches (se
     return dbg ? atoi(dbg) : 0;
 }
 
+static int tc_epilogue_variant() {  // BPMF_TC_EPI=0 selects the shuffle-transpose epilogue (A/B measurements)
+    const char *e = getenv("BPMF_TC_EPI");
+    return (e && atoi(e) == 0) ? 0 : 1;
+}
+
 bool mf_tc_supported(size_t L, size_t step, int normalize, int network_sum) {
     return step == 1 && normalize == 0 && network_sum != 0 && L >= 8 && L <= 65536;
 }
@@ -672,6 +832,7 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
                  "matched filter: shape not supported by the tensor path");
     BPMF_REQUIRE(!split || traces_have_lo, "matched filter: traces were prepared without the lo part");
     const TcGeom g = tc_geom(sh, split);
+    const int epi = tc_epilogue_variant();
     TcTraceWs tw = tc_carve_traces(trace_ws, sh, tc_geom(sh, 0), traces_have_lo);
     TcTplWs w = tc_carve_templates(tpl_ws, sh, g);
     BPMF_REQUIRE(trace_ws.ok() && tpl_ws.ok(), "matched filter: workspace too small for the tensor path");
@@ -682,7 +843,7 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     tc_template_prep_kernel<<<dim3((unsigned)w.MT, (unsigned)SC), TC_ROWS, 0, st>>>(
         d_templates, d_moveouts, d_weights, meta.sst, meta.lo, meta.hi, tw.ch_scale, (int)sh.T, (int)SC, (int)sh.L,
         g.n_kc, g.Kc, split, g.a_bytes, g.a_img_bytes, w.aimg, w.row_q, w.row_e, w.row_scale, w.row_ithr,
-        w.item_active, tc_debug_flags());
+        w.item_active, tc_debug_flags(), epi);
     BPMF_LAUNCH_CHECK();
     // cc_sum is accumulated with reductions: start from zero (also the value of never-computed outputs)
     BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * cc_pitch, st));
@@ -705,13 +866,14 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     p.debug = tc_debug_flags();
     const long long n_items = (long long)p.n_seg * p.MT * p.SC * p.n_kc;
     BPMF_REQUIRE(n_items < (1ll << 31), "matched filter: too many work items for the tensor path");
-    BPMF_CUDA(cudaFuncSetAttribute(mf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    auto kern = epi ? mf_tc_kernel<1> : mf_tc_kernel<0>;
+    BPMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     // persistent grid: one CTA per SM, minus the SMs the caller reserved for a concurrent collective
     const int sms = std::max(1, num_sms() - reserved_sms());
     const int grid = (int)std::min<long long>(n_items, (long long)sms);
     {
         MainKernelTimer timer(st);
-        mf_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, st>>>(p);
+        kern<<<grid, TC_THREADS, g.smem_bytes, st>>>(p);
     }
     BPMF_LAUNCH_CHECK();
     return BPMF_OK;

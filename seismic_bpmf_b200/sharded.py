@@ -55,19 +55,18 @@ def _matched_filter_sharded_overlapped(templates, moveouts, weights, data, step,
     if hi > lo:
         plan.prepare(data)
     empty = torch.zeros(0, dtype=torch.float32, device=data.device)
-    pending = []
     for b, t0 in enumerate(range(0, rows, batch)):
         n_here = max(0, min(batch, (hi - lo) - t0))
-        if b >= 2:  # buffer b % 2 is about to be refilled: lay out the batch it still holds
-            _scatter_gathered(out, gather, *pending.pop(0), T, world, pitch, n_corr)
         if n_here > 0:
             plan.run_batch(tp, mv, w, data, t0, n_here)
             gather.push(b % 2, plan.cc[t0: t0 + n_here].reshape(-1))
         else:
             gather.push(b % 2, empty)  # short shard: still take part in the batch barrier
-        pending.append((b % 2, t0))
-    for item in pending:
-        _scatter_gathered(out, gather, *item, T, world, pitch, n_corr)
+        # Lay the batch out in template order RIGHT BEHIND its own barrier on the ordering stream.  A peer's push
+        # of batch b + 2 into this same buffer waits for barrier b + 1 of its own ordering stream, and that
+        # barrier completes only once this rank has arrived at it -- i.e. after this read: no peer, however far
+        # ahead, can overwrite the buffer while it is still being read here.
+        _scatter_gathered(out, gather, b % 2, t0, T, world, pitch, n_corr)
     torch.cuda.current_stream().wait_stream(gather.stream)
     return out
 

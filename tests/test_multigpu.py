@@ -36,6 +36,24 @@ def _worker(rank, world, port, ret):
         want = cpu.matched_filter(tp, mv, w, d, 1)
         ok_mf = float(np.abs(got.cpu().numpy() - want).max()) < 2e-6
 
+        # the same through many small batches with one rank lagging: its peer runs ahead and must not overwrite a
+        # gather buffer this rank is still laying out (double-buffer ordering of PeerSlabGather)
+        from seismic_bpmf_b200 import device as devmod
+
+        if rank == 1:
+            plain = devmod.MatchedFilterPlan.run_batch
+
+            def slow(self, *a, **k):
+                torch.cuda._sleep(int(4e7))  # ~20 ms in front of every batch of this rank
+                return plain(self, *a, **k)
+
+            devmod.MatchedFilterPlan.run_batch = slow
+        got = sharded.matched_filter_sharded(*(torch.from_numpy(a).to(dev) for a in (tp, mv, w, d)), precision="fp32",
+                                             batch=3)
+        ok_mf = ok_mf and float(np.abs(got.cpu().numpy() - want).max()) < 2e-6
+        if rank == 1:
+            devmod.MatchedFilterPlan.run_batch = plain
+
         f, tau, wp, ws = _synth.beam_case(301, 6, 2, 2, 9000, seed=42)
         tau[200], ws[200] = tau[100], ws[100]  # a tie across the shard boundary
         mb, am = sharded.beamform_max_sharded(torch.from_numpy(f).to(dev), torch.from_numpy(tau.astype(np.int32)).to(dev),
