@@ -16,6 +16,12 @@ metric = CC-sum GSamples/s = templates x channels x n_corr / seconds / 1e9.
   value : inputs resident in HBM when the timed region starts (device entry point, CUDA events).
   e2e   : same metric through the reference-facing call fast_matched_filter.matched_filter(...) with
           pinned HOST buffers, host<->device copies inside the timed region.
+Extra objects on the same JSON line (each leg is untimed by the contract and can be switched off):
+  parity      strided comparison with the CPU oracle over the whole day, every template tile (tests/_parity.py)
+  variants    SURVEY 8(d)'s second weighting (10 smallest-moveout stations per template): value + parity
+  cfg4        BASELINE.json configs[3], 5000 x 32 x 3 strong-scaled over the N ranks (tools/bench_cfg4.py)
+  beamform    the second hot path: device figure + roofline, host-API e2e, CPU baseline; N > 1: source-sharded
+  libc        the libc.so rows against the reference's own compiled libc.c (tools/bench_libc.py)
 """
 import argparse
 import ctypes as C
@@ -48,6 +54,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", help="skip the beamforming figure")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the 5000-template strong-scaling leg")
+    ap.add_argument("--no-libc", action="store_true", help="skip the libc.so rows")
+    ap.add_argument("--no-variants", action="store_true", help="skip the second weighting variant")
+    ap.add_argument("--no-parity", action="store_true", help="skip the strided oracle comparison")
+    ap.add_argument("--cfg4-steps", type=int, default=2)
     ap.add_argument("--callers", action="store_true",
                     help="also time the SURVEY 8(f) rows (moveout tables, detection traces, inter-template CC) against "
                          "their CPU restatements on bounded samples (adds ~1 min; off by default)")
@@ -67,59 +78,8 @@ def peaks():
                 source="fallback")
 
 
-# ------------------------------------------------------------------ clocks sampler
-class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                pw.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from clocks import ClockSampler  # noqa: E402
 
 
 # ------------------------------------------------------------------ synthetic workload
@@ -176,6 +136,7 @@ def cpu_sample_throughput(seconds, S, Cc, L, seed=SEED):
     length are scaled from a calibration run so the sample takes about `seconds`."""
     from oracle import cpu
 
+    native = cpu.use_native()  # built on this host with the reference's flags, -march=native included
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(seed)
 
@@ -195,7 +156,13 @@ def cpu_sample_throughput(seconds, S, Cc, L, seed=SEED):
     T = int(max(1, min(64, units / (S * Cc * (N - L + 1)))))
     rate, dt = run(T, N)
     return rate, cores, "%d templates x %d stations x %d channels x %d samples (L=%d, step 1), %.1f s" % (
-        T, S, Cc, N, L, dt)
+        T, S, Cc, N, L, dt), (cpu.build_kind if native else "portable (-march=x86-64-v3)")
+
+
+def cpu_model():
+    from oracle import build as ob
+
+    return ob.cpu_model()
 
 
 def run_reference(args, rank):
@@ -205,7 +172,7 @@ def run_reference(args, rank):
     rates, sample = [], ""
     per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
-        rate, cores, sample = cpu_sample_throughput(per_step, S, Cc, L, seed=SEED + i)
+        rate, cores, sample, build = cpu_sample_throughput(per_step, S, Cc, L, seed=SEED + i)
         if i >= args.warmup:
             rates.append(rate)
     value = float(np.mean(rates))
@@ -217,7 +184,8 @@ def run_reference(args, rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "matched_filter cfg2: %d templates x %d stations x %d ch, L=%d, N=%d, step 1"
                    % (T, S, Cc, L, N), "note": "ms_per_step extrapolated from the bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "GSamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GSamples/s", "cores": cores, "kind": "port", "sample": sample,
+                         "build": build, "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "GSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -294,6 +262,41 @@ def callers_figures():
 
 
 # ------------------------------------------------------------------ our arm
+def ten_closest_weights(torch, moveouts, keep=10):
+    """SURVEY 8(d), second variant: only the `keep` smallest-moveout stations of every template carry weight
+    (mirrors N_SELECTED_STATIONS = 10, tutorial 8_template_matching.ipynb:90), rows normalised to sum 1."""
+    T, S, Cc = moveouts.shape
+    order = moveouts.min(dim=2).values.argsort(dim=1)
+    w = torch.zeros((T, S, Cc), device=moveouts.device, dtype=torch.float32)
+    w.scatter_(1, order[:, :keep].unsqueeze(-1).expand(T, keep, Cc), 1.0)
+    return (w / w.sum(dim=(1, 2), keepdim=True)).contiguous()
+
+
+def strided_parity(torch, plan, tp, mv, w, data_host, planted, N, L, n_windows=64, win_len=2048):
+    """Untimed: the CC slab the timed passes left in HBM against the CPU oracle on runs of `win_len` outputs spread
+    over the whole day, for three templates of every 16-template tile plus every planted template."""
+    from oracle import cpu
+    from tests import _parity
+
+    n_corr = plan.n_corr
+    T = tp.shape[0]
+    sel = _parity.tile_templates(T, per_tile=3, extra=planted.keys())
+    starts = _parity.window_starts(n_corr, n_windows, win_len, gap=(N // 3, N // 3 + 10000), planted=planted.values(), L=L)
+    idx = torch.from_numpy(starts).to(plan.cc.device).reshape(-1, 1) + torch.arange(win_len, device=plan.cc.device)
+    sel_d = torch.from_numpy(sel).to(plan.cc.device)
+    got = plan.cc[sel_d][:, idx.reshape(-1)].reshape(len(sel), len(starts), win_len).cpu().numpy()
+    t0 = time.perf_counter()
+    want = cpu.matched_filter_windows(tp[sel_d].cpu().numpy(), mv[sel_d].cpu().numpy(), w[sel_d].cpu().numpy(), data_host,
+                                      starts, win_len, num_threads=os.cpu_count() or 1)
+    rec = _parity.compare(got, want)
+    ok_plant = all(int(torch.argmax(plan.cc[t, :n_corr]).item()) == i0 for t, i0 in planted.items())
+    rec.update({"planted_detections_recovered": bool(ok_plant), "oracle_seconds": time.perf_counter() - t0,
+                "sample": "%d templates (3 of each of the %d tiles of 16 + the planted ones) x %d runs of %d outputs over "
+                          "[0, n_corr): first / last outputs, segment boundaries, the zero gap, planted indices, seeded "
+                          "random positions" % (len(sel), (T + 15) // 16, len(starts), win_len)})
+    return rec
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -311,6 +314,14 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def guarded(fn, *a, **k):
+        """An extra figure must never break the contract line."""
+        try:
+            return fn(*a, **k)
+        except Exception as exc:  # noqa: BLE001
+            torch.cuda.synchronize()
+            return {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
 
     # rank r owns templates [r*T, (r+1)*T) of the global 500*N set: different seeds per rank
     tp, mv, w, data, planted = make_inputs_device(torch, T, S, Cc, L, N, SEED + rank, device)
@@ -338,14 +349,15 @@ def run_ours(args, rank, world, local_rank):
             gbufs = [torch.empty(world * batch * plan.pitch, dtype=torch.float32, device=device) for _ in range(2)]
             collective = "NCCL all-gather of per-shard CC slabs, one per %d-template batch" % batch
 
-    def step_fn():
+    def step_fn(weights=None):
+        ww = w if weights is None else weights
         if world == 1:
-            return plan.run(tp, mv, w, data)
+            return plan.run(tp, mv, ww, data)
         plan.prepare(data)
         works = []
         for b, t0 in enumerate(range(0, T, batch)):
             rows = min(batch, T - t0)
-            plan.run_batch(tp, mv, w, data, t0)
+            plan.run_batch(tp, mv, ww, data, t0)
             src = plan.cc[t0: t0 + rows].reshape(-1)
             if gather is not None:
                 gather.push(b % 2, src)
@@ -359,52 +371,50 @@ def run_ours(args, rank, world, local_rank):
             wk.wait()
         return plan.cc
 
-    for _ in range(args.warmup):
-        step_fn()
-    barrier()
+    def timed(n_steps, n_warm, weights=None, with_clocks=False):
+        """(ms per step [max over ranks], main-kernel ms per step on this rank, launches per step, clocks)."""
+        for _ in range(n_warm):
+            step_fn(weights)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if with_clocks and rank == 0:
+            sampler.start()
+        lib.bpmf_set_kernel_timing(1)
+        lib.bpmf_main_kernel_times((C.c_float * 256)(), 256)  # drain earlier records
+        launches0 = lib.bpmf_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(n_steps):
+            step_fn(weights)
+        ev1.record()
+        barrier()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        launches = int(lib.bpmf_launch_count() - launches0)
+        buf = (C.c_float * 256)()
+        nk = lib.bpmf_main_kernel_times(buf, 256)
+        lib.bpmf_set_kernel_timing(0)
+        # one record per kernel launch (= per template batch at N > 1): the step's kernel time is their SUM / steps
+        complete = nk == n_steps * ((T + batch - 1) // batch)
+        kernel_ms = float(sum(buf[i] for i in range(nk))) / n_steps if (nk and complete) else None
+        clocks = sampler.stop() if (with_clocks and rank == 0) else None
+        t_ms = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return float(t_ms.item()) / n_steps, kernel_ms, launches // max(1, n_steps), clocks
+
+    ms_per_step, kernel_ms, launches, clocks = timed(args.steps, args.warmup, with_clocks=True)
     prec_name = {1: "fp32", 2: "fp16", 3: "fp16x3"}[plan.last_precision]
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    lib.bpmf_set_kernel_timing(1)
-    launches0 = lib.bpmf_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step_fn()
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = int(lib.bpmf_launch_count() - launches0)
-    buf = (C.c_float * 256)()
-    nk = lib.bpmf_main_kernel_times(buf, 256)
-    lib.bpmf_set_kernel_timing(0)
-    kernel_ms = float(np.mean([buf[i] for i in range(nk)])) if nk else None
-    clocks = sampler.stop() if rank == 0 else None
-
-    t_ms = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t_ms.item()) / args.steps
     value = world * units / (ms_per_step * 1e-3) / 1e9
+    if clocks is not None and kernel_ms is None:
+        clocks["note"] = "main-kernel event ring incomplete"
 
-    # ---- parity spot check (untimed): first template against the oracle on a trace slice
+    # ---- parity (untimed): strided comparison with the oracle over the whole day, every template tile
     parity = None
-    if rank == 0:
-        from oracle import cpu
-
-        n_slice = min(N, 200000)
-        cc_dev = plan.cc[:2, :n_corr].cpu().numpy()
-        want = cpu.matched_filter(tp[:2].cpu().numpy(), mv[:2].cpu().numpy(), w[:2].cpu().numpy(),
-                                  data[:, :, :n_slice].cpu().numpy(), 1)
-        hi = n_slice - L - int(mv[:2].max().item()) - 1
-        lo = max(0, -int(mv[:2].min().item()))
-        err = float(np.abs(cc_dev[:, lo:hi] - want[:, lo:hi]).max())
-        ok_plant = all(int(torch.argmax(plan.cc[t, :n_corr]).item()) == i0 for t, i0 in planted.items())
-        parity = {"max_abs_err_vs_oracle": err, "tolerance": 1e-4, "planted_detections_recovered": bool(ok_plant),
-                  "sample": "templates 0-1 x first %d samples" % n_slice}
+    data_host = None
+    if rank == 0 and not args.no_parity:
+        data_host = data.cpu().numpy()
+        parity = guarded(strided_parity, torch, plan, tp, mv, w, data_host, planted, N, L)
 
     # ---- exchange spot check (untimed): the last batch of every rank arrived in this rank's gather buffer
     if world > 1 and gather is not None:
@@ -417,59 +427,73 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         got = gather.gathered((n_batches - 1) % 2, rows, plan.pitch).double().sum(dim=(1, 2))
         ok = bool(torch.allclose(got, sums, rtol=1e-9, atol=1e-6))
-        if parity is not None:
+        if isinstance(parity, dict):
             parity["gathered_slabs_match"] = ok
 
-    # ---- fused-workflow figure (extra, untimed by the contract): traces + templates from pinned host memory,
-    # matched filter, rms threshold + declustering + compaction on the device, only the
-    # detections come back -- what replaces similarity_search.py:526-666 when BPMF keeps the CC on the GPU
+    # ---- SURVEY 8(d) second weighting: the 10 smallest-moveout stations of every template (N = 1)
+    variants = None
+    if world == 1 and not args.no_variants:
+        def second_variant():
+            w2 = ten_closest_weights(torch, mv, keep=min(10, S))
+            ms2, k2, _, _ = timed(3, 2, weights=w2)
+            units2 = T * int((w2[0] != 0).sum().item()) * n_corr
+            rec = {"weights": "10 smallest-moveout stations per template, row-normalised",
+                   "weighted_channels_per_template": int((w2[0] != 0).sum().item()), "ms_per_step": ms2,
+                   "value": units2 / (ms2 * 1e-3) / 1e9, "unit": "GSamples/s (weighted channels only, SURVEY 8d)",
+                   "precision": {1: "fp32", 2: "fp16", 3: "fp16x3"}[plan.last_precision], "kernel_ms": k2}
+            if k2:
+                rec["tensor_frac"] = 2.0 * L * units2 / (k2 * 1e-3) / 1e12 / pk["tensor_tflops_sustained"]
+            if data_host is not None:
+                rec["parity"] = strided_parity(torch, plan, tp, mv, w2, data_host, planted, N, L, n_windows=24)
+            return rec
+
+        variants = {"ten_closest_stations": guarded(second_variant)}
+        step_fn()  # leave the all-stations result in the slab for the legs below
+        torch.cuda.synchronize()
+    del data_host
+
+    # ---- fused detection (the product path when the caller keeps the CC on the device): traces + templates from
+    # pinned host memory, matched filter, rms threshold + declustering + compaction on the device, only
+    # the detections come back -- what replaces similarity_search.py:526-666.  At N > 1 every rank does this for its
+    # own templates and the detections are all-gathered.
     fused = None
-    if world == 1 and not args.no_e2e:
-        try:
+    if not args.no_e2e:
+        def fused_leg():
+            from seismic_bpmf_b200 import sharded
+
             hp = [torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_) for t_ in (tp, mv, w, data)]
             gauss = torch.randn(500, generator=torch.Generator().manual_seed(1)).pin_memory()
             win = 180000  # 30 min @ 100 Hz, overlap 0.25 as BPMF's callers pass (similarity_search.py:552)
-            torch.cuda.synchronize()
-            t_fused = []
-            for _ in range(3):
+            det = dev.DetectBatches(1, T, n_corr, win // 2, int(0.75 * win), capacity=1 << 22, device=device)
+            times = []
+            for it in range(4):
+                barrier()
                 t0_ = time.perf_counter()
                 dv = [h_.to(device, non_blocking=True) for h_ in hp]
                 plan.run(*dv)
-                s_, i_, v_, th_ = dev.detect_dev(plan.cc, gauss.to(device, non_blocking=True), 8.0, win // 2,
-                                                 int(0.75 * win), search_win=6000, mode="select",
-                                                 n_valid=n_corr, capacity=1 << 22)
-                t_fused.append(time.perf_counter() - t0_)
-            dt_f = float(np.median(t_fused))
+                det.run(0, plan.cc, gauss.to(device, non_blocking=True), 8.0, search_win=6000, mode="select")
+                s_, i_, v_, th_ = det.collect(series_offsets=[rank * T])
+                if world > 1:
+                    s_, i_, v_, th_ = sharded.gather_detections(s_, i_, v_, th_, device=device)
+                torch.cuda.synchronize()
+                if it:
+                    times.append(time.perf_counter() - t0_)
+            t_f = torch.tensor([float(np.median(times))], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_f, op=dist.ReduceOp.MAX)
+            dt_f = float(t_f.item())
             hit = all(((s_ == t_) & (i_ == i0)).any() for t_, i0 in planted.items())
-            fused = {"value": units / dt_f / 1e9, "unit": "GSamples/s", "ms_per_step": 1e3 * dt_f,
-                     "detections": int(len(s_)), "planted_detections_found": bool(hit),
-                     "d2h_bytes_per_step": int(16 * len(s_) + 4),
-                     "what": "H2D inputs + matched filter + device threshold/declustering/compaction + D2H of detections"}
-            del dv, hp
-        except Exception as exc:  # noqa: BLE001 -- an extra figure must never break the contract line
-            fused = {"error": str(exc)[:200]}
+            return {"value": world * units / dt_f / 1e9, "unit": "GSamples/s", "ms_per_step": 1e3 * dt_f,
+                    "detections": int(len(s_)), "planted_detections_found": bool(hit),
+                    "h2d_bytes_per_step": int(sum(h_.numel() * h_.element_size() for h_ in hp)),
+                    "d2h_bytes_per_step": int(16 * len(s_) + 4),
+                    "what": "H2D inputs + matched filter + device threshold/declustering/compaction + D2H"
+                            + (" + all-gather" if world > 1 else "") + " of detections"}
 
-    # ---- second hot path (extra object): beamforming / backprojection, BASELINE.json configs[2] scaled to a
-    # few seconds (the full 1e6-source x 1-day grid is ~1 minute per pass): source.samples/s and the
-    # shared-memory roofline fraction of SURVEY.md 8(d)
-    beam = None
-    if world == 1 and not args.no_beam:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_beam
+        fused = guarded(fused_leg)
 
-            beam = bench_beam.run(K=50000, N=432000, S=32, keep=32, steps=3, warmup=2, device_index=local_rank)
-        except Exception as exc:  # noqa: BLE001 -- an extra figure must never break the contract line
-            beam = {"error": str(exc)[:200]}
-
-    callers = None
-    if world == 1 and args.callers:
-        try:
-            callers = callers_figures()
-        except Exception as exc:  # noqa: BLE001
-            callers = {"error": str(exc)[:300]}
-
-    # ---- end-to-end arm: the reference-facing call with pinned host buffers
+    # ---- end-to-end arm: the reference-facing call with pinned host buffers.  At N > 1 every rank's host process
+    # holds its own block of templates and receives its own (T/N, n_corr) block of CC.
     e2e = None
     if not args.no_e2e:
         h = {}
@@ -504,14 +528,76 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * units / float(t_e.item()) / 1e9, "unit": "GSamples/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-               "ms_per_step": 1e3 * float(t_e.item()), "host_buffers": host_kind}
+               "ms_per_step": 1e3 * float(t_e.item()), "host_buffers": host_kind,
+               "aggregate_d2h_gbs": world * d2h / float(t_e.item()) / 1e9}
+        if world > 1:
+            e2e["note"] = ("every rank's process downloads its own (T/N, n_corr) block into pinned host memory: the figure "
+                           "is bounded by the host's aggregate ingest (aggregate_d2h_gbs), see e2e_fused_detection for the "
+                           "path that returns detections instead of the CC slab")
+        bpmf_release = getattr(lib, "bpmf_release_cache", None)
+        if bpmf_release:
+            bpmf_release()
+        del h, out_np
+    else:
+        del plan
+        gbufs = gather = None
+    del tp, mv, w, data
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[3]: 5000 x 32 x 3 strong-scaled over the ranks
+    cfg4 = None
+    if not args.no_cfg4:
+        import bench_cfg4
+
+        cfg4 = guarded(bench_cfg4.run, rank, world, device, steps=args.cfg4_steps, warmup=1, precision=args.precision,
+                       T=(None if args.templates == CFG2["T"] else 10 * args.templates // 125 * 125 or 125),
+                       samples=(None if args.samples == CFG2["N"] else args.samples))
+        torch.cuda.empty_cache()
+
+    # ---- second hot path: beamforming / backprojection, BASELINE.json configs[2] scaled to a few seconds (the full
+    # 1e6-source x 1-day grid is ~1 minute per pass: profiles/): device figure + shared-memory roofline,
+    # the host-API call BPMF makes, the CPU oracle; at N > 1 the source-sharded strong-scaling leg
+    beam = None
+    if not args.no_beam:
+        import bench_beam
+
+        if world == 1:
+            beam = guarded(bench_beam.run, K=50000, N=432000, S=32, keep=32, steps=3, warmup=2, device_index=local_rank)
+            if isinstance(beam, dict) and "error" not in beam:
+                beam["ten_closest_stations"] = guarded(
+                    lambda: {k: v for k, v in bench_beam.run(K=50000, N=432000, S=32, keep=10, steps=3, warmup=2,
+                                                             device_index=local_rank).items()
+                             if k in ("ms_per_step", "kernel_ms", "G_source_samples_per_s", "G_gather_fma_per_s", "roofline")})
+                beam["e2e"] = guarded(bench_beam.e2e_host_api, K=50000, N=432000, S=32, steps=2)
+                if not args.no_cpu_baseline:
+                    beam["cpu_baseline"] = guarded(bench_beam.cpu_baseline, seconds=8.0, S=32)
+        beam_sh = guarded(bench_beam.run_sharded, K=200000, N=432000, S=32, steps=3, warmup=2, rank=rank, world=world,
+                          device_index=local_rank)
+        if beam is None:
+            beam = {}
+        beam["sharded"] = beam_sh
+
+    callers = None
+    if world == 1 and args.callers:
+        callers = guarded(callers_figures)
 
     if rank != 0:
         return
+    libc = None
+    if world == 1 and not args.no_libc:
+        import bench_libc
+
+        def libc_leg():
+            with bench_libc._quiet():  # the reference (and the drop-in, like it) print progress with printf
+                return bench_libc.run(device_index=local_rank)
+
+        libc = guarded(libc_leg)
+
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, cores, sample = cpu_sample_throughput(args.cpu_seconds, S, Cc, L)
-        cpu_base = {"value": rate, "unit": "GSamples/s", "cores": cores, "kind": "port", "sample": sample}
+        rate, cores, sample, build = cpu_sample_throughput(args.cpu_seconds, S, Cc, L)
+        cpu_base = {"value": rate, "unit": "GSamples/s", "cores": cores, "kind": "port", "sample": sample,
+                    "build": build, "cpu_model": cpu_model()}
 
     flops = 2.0 * L * units
     roof = None
@@ -524,7 +610,9 @@ def run_ours(args, rank, world, local_rank):
                     "unit": "TFLOP/s", "frac": tflops * mult / pk["tensor_tflops_sustained"],
                     "traffic": measured_traffic("mf_tc_kernel", T, S, Cc, L, N),
                     "peak_source": pk["source"] + " (sustained bf16 cuBLAS; fp16 runs at the same tensor rate)",
-                    "algorithmic_tflops": tflops, "kernel_ms": kernel_ms, "kernel": "mf_tc_kernel"}
+                    "algorithmic_tflops": tflops, "kernel_ms": kernel_ms, "kernel": "mf_tc_kernel",
+                    "kernel_ms_is": "sum of the main-kernel launches of one step on rank 0 (%d per step)" % ((T + batch - 1) // batch),
+                    "frac_of_burst_peak": tflops * mult / pk["tensor_tflops"]}
         else:
             sm_mhz = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
             peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -543,10 +631,12 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "matched_filter cfg2 per GPU: %d templates x %d stations x %d ch, L=%d, N=%d, step 1"
                    % (T, S, Cc, L, N), "precision": prec_name, "templates_total": T * world,
                    "l2": "inputs (%.2f GB) and output (%.2f GB) exceed the 126 MB L2" % (
-                       (data.numel() * 4 + tp.numel() * 4) / 1e9, T * n_corr * 4 / 1e9),
-                   "collective": collective},
-        "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "parity": parity, "e2e_fused_detection": fused, "beamform": beam,
+                       (S * Cc * N * 4 + T * S * Cc * L * 4) / 1e9, T * n_corr * 4 / 1e9),
+                   "collective": collective,
+                   "epilogue": "shuffle-free (16x128b TMEM loads, red.v2)" if os.environ.get("BPMF_TC_EPI", "1") != "0"
+                   else "r1 (32x32b TMEM loads, butterfly transpose, red.v4)"},
+        "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks,
+        "parity": parity, "variants": variants, "e2e_fused_detection": fused, "cfg4": cfg4, "beamform": beam, "libc": libc,
     }
     if callers is not None:
         line["callers"] = callers

@@ -38,6 +38,48 @@ def build_oracle(force=False, verbose=False):
     return out
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build_oracle_native(verbose=False):
+    """The same two restatements compiled ON THIS HOST with the reference's own flags, ``-march=native`` included
+    (Makefile:20,24-25) -- what bench.py times as the CPU baseline on the GPU box.  The artefact is tagged with
+    the CPU model and never reused on another host.  Returns the path, or None when gcc is missing."""
+    import hashlib
+
+    srcs = [os.path.join(HERE, "mf_oracle.c"), os.path.join(HERE, "beam_oracle.c")]
+    feats = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                feats = ln
+                break
+    except OSError:
+        pass
+    tag = hashlib.sha1((cpu_model() + feats + os.uname().nodename).encode()).hexdigest()[:10]
+    out_dir = os.path.join(HERE, "_native")
+    out = os.path.join(out_dir, "liboracle-%s.so" % tag)
+    if _newer(out, srcs):
+        return out
+    os.makedirs(out_dir, exist_ok=True)
+    flags = [f if f != "-march=x86-64-v3" else "-march=native" for f in CFLAGS]
+    cmd = ["gcc"] + flags + srcs + ["-o", out, "-lm"]
+    if verbose:
+        print(" ".join(cmd))
+    try:
+        subprocess.check_call(cmd, stderr=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        return None
+    return out
+
+
 def build_ref(force=False, verbose=False):
     """Compile the reference's libc.c -> oracle/_ref/libc.so (only where /root/reference exists)."""
     out_dir = os.path.join(HERE, "_ref", "lib")

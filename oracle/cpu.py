@@ -11,20 +11,38 @@ import numpy as np
 from . import build as _build
 
 _lib = None
+_path = None
+build_kind = "portable (-march=x86-64-v3, built in the CPU container)"
+
+
+def use_native():
+    """Switch to a build of the same sources made on THIS host with -march=native (bench.py's CPU legs).
+    Returns True when the native build is in use."""
+    global _lib, _path, build_kind
+    path = _build.build_oracle_native()
+    if path is None:
+        return False
+    if path != _path:
+        _lib, _path = None, path
+        build_kind = "native (-O3 -fopenmp -ftree-vectorize -march=native, built on this host: %s)" % _build.cpu_model()
+    return True
 
 
 def lib():
-    global _lib
+    global _lib, _path
     if _lib is None:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboracle.so")
+        path = _path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboracle.so")
         if not os.path.exists(path):
             _build.build_oracle()
+        _path = path
         _lib = C.cdll.LoadLibrary(path)
         fp, ip, llp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)
         z = C.c_size_t
         _lib.oracle_matched_filter.argtypes = [fp, ip, fp, fp, z, z, z, z, z, z, z, C.c_int,
                                                C.c_int, C.c_int, fp]
         _lib.oracle_matched_filter.restype = C.c_int
+        _lib.oracle_matched_filter_windows.argtypes = [fp, ip, fp, fp, z, z, z, z, z, z, llp, z, C.c_int, fp]
+        _lib.oracle_matched_filter_windows.restype = C.c_int
         _lib.oracle_beamform.argtypes = [fp, llp, fp, fp, z, z, z, z, z, C.c_int, C.c_int, C.c_int,
                                          fp, ip, fp]
         _lib.oracle_beamform.restype = C.c_int
@@ -57,6 +75,24 @@ def matched_filter(templates, moveouts, weights, data, step, normalize="short", 
                                      1 if network_sum else 0, num_threads, _p(out, C.c_float))
     if rc != 0:
         raise MemoryError("oracle_matched_filter failed")
+    return out
+
+
+def matched_filter_windows(templates, moveouts, weights, data, win_start, win_len, num_threads=0):
+    """cc_sum[t, win_start[w] + x] for x < win_len (step 1, "short" normalisation, network sum), without
+    computing the rest of the (T, n_corr) slab -- parity checks at full day length."""
+    templates, weights, data = _f32(templates), _f32(weights), _f32(data)
+    T, S, Cc, L = templates.shape
+    N = data.shape[-1]
+    moveouts = np.ascontiguousarray(moveouts, dtype=np.int32)
+    win_start = np.ascontiguousarray(win_start, dtype=np.int64)
+    out = np.zeros((T, len(win_start), int(win_len)), dtype=np.float32)
+    rc = lib().oracle_matched_filter_windows(_p(templates, C.c_float), _p(moveouts, C.c_int), _p(weights, C.c_float),
+                                             _p(data, C.c_float), L, N, T, S, Cc, len(win_start),
+                                             _p(win_start, C.c_longlong), int(win_len), num_threads,
+                                             _p(out, C.c_float))
+    if rc != 0:
+        raise MemoryError("oracle_matched_filter_windows failed")
     return out
 
 

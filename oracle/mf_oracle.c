@@ -138,3 +138,80 @@ int oracle_matched_filter(const float *templates, const int *moveouts, const flo
     free(csum); free(csum2); free(sst); free(sumt);
     return 0;
 }
+
+/*
+ * Same semantics (step 1, "short" normalisation, network sum), evaluated only on selected runs of output
+ * indices: out[t, w, x] = cc_sum[t, win_start[w] + x] for x < win_len (0 where the index is outside
+ * [0, n_corr) or outside the template's valid range).  Used by the parity checks at full day length, where
+ * the whole (T, n_corr) slab is hours of CPU work: the window energies are accumulated directly in double
+ * precision (first window of a run: L terms; then one term in, one term out), no O(S*C*N) prefix arrays.
+ */
+int oracle_matched_filter_windows(const float *templates, const int *moveouts, const float *weights,
+                                  const float *data, size_t L, size_t N, size_t T, size_t S, size_t C,
+                                  size_t n_win, const long long *win_start, size_t win_len, int num_threads,
+                                  float *out) {
+    const size_t SC = S * C;
+    if (num_threads > 0) omp_set_num_threads(num_threads);
+    if (N < L) return 0;
+    const long n_corr = (long)(N - L + 1);
+    const size_t SUB = 32768; /* runs are cut into pieces so that a few long runs still use every core */
+    const size_t n_sub = (win_len + SUB - 1) / SUB;
+    float *sst = (float *)malloc(sizeof(float) * T * SC);
+    if (!sst) return -1;
+#pragma omp parallel for
+    for (size_t q = 0; q < T * SC; q++) {
+        double a = 0.0;
+        for (size_t k = 0; k < L; k++) {
+            double v = (double)templates[q * L + k];
+            a += v * v;
+        }
+        sst[q] = (float)a;
+    }
+    memset(out, 0, sizeof(float) * T * n_win * win_len);
+#pragma omp parallel for schedule(dynamic) collapse(3)
+    for (size_t t = 0; t < T; t++) {
+        for (size_t w = 0; w < n_win; w++) {
+            for (size_t sb = 0; sb < n_sub; sb++) {
+                long min_mv = 0, max_mv = 0;
+                int any = 0;
+                for (size_t ch = 0; ch < SC; ch++) {
+                    if (weights[t * SC + ch] == 0.f) continue;
+                    long m = moveouts[t * SC + ch];
+                    if (!any) { min_mv = max_mv = m; any = 1; }
+                    if (m < min_mv) min_mv = m;
+                    if (m > max_mv) max_mv = m;
+                }
+                if (!any) continue;
+                long n_lo = min_mv < 0 ? -min_mv : 0;
+                long n_hi = (long)N - (long)L - max_mv; /* inclusive, as oracle_matched_filter */
+                if (n_hi > n_corr - 1) n_hi = n_corr - 1;
+                long a = (long)win_start[w] + (long)(sb * SUB);
+                long b = a + (long)((win_len - sb * SUB < SUB) ? win_len - sb * SUB : SUB) - 1;
+                float *o = out + (t * n_win + w) * win_len + sb * SUB - a; /* o[n] for n in [a, b] */
+                if (a < n_lo) a = n_lo;
+                if (b > n_hi) b = n_hi;
+                if (b < a) continue;
+                for (size_t ch = 0; ch < SC; ch++) {
+                    const float wgt = weights[t * SC + ch];
+                    if (wgt == 0.f) continue;
+                    const float *tp = templates + (t * SC + ch) * L;
+                    const float *d = data + ch * N;
+                    const long mv = moveouts[t * SC + ch];
+                    double ssd = 0.0;
+                    for (size_t k = 0; k < L; k++) ssd += (double)d[a + mv + (long)k] * (double)d[a + mv + (long)k];
+                    for (long n = a; n <= b; n++) {
+                        const long j = n + mv;
+                        const float num = dotf(tp, d + j, L);
+                        const float den = sst[t * SC + ch] * (float)ssd;
+                        float cc = 0.f;
+                        if (den > MF_STABILITY_GUARD) cc = num / sqrtf(den);
+                        o[n] += wgt * cc;
+                        if (n < b) ssd += (double)d[j + (long)L] * (double)d[j + (long)L] - (double)d[j] * (double)d[j];
+                    }
+                }
+            }
+        }
+    }
+    free(sst);
+    return 0;
+}

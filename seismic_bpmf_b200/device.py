@@ -78,16 +78,18 @@ class MatchedFilterPlan:
                                                  self.trace_ws.data_ptr(), self.trace_ws.numel(), _stream_ptr())
         _lib.check(rc, "mf_prepare_traces_dev")
 
-    def run_batch(self, templates, moveouts, weights, data, t0=0, n=None):
-        """Templates [t0, t0+n) of the (T,...) inputs into rows [t0, t0+n) of the CC slab."""
-        n = min(self.batch, self.T - t0) if n is None else int(n)
-        assert 0 < n <= self.batch and t0 + n <= self.T
+    def run_batch(self, templates, moveouts, weights, data, t0=0, n=None, cc_row0=None):
+        """Templates [t0, t0+n) of the inputs into rows [cc_row0, cc_row0+n) of the CC slab (default: the same
+        rows [t0, t0+n); a caller that streams more templates than the slab holds passes its own slot)."""
+        n = min(self.batch, templates.shape[0] - t0) if n is None else int(n)
+        r0 = t0 if cc_row0 is None else int(cc_row0)
+        assert 0 < n <= self.batch and t0 + n <= templates.shape[0] and r0 + n <= self.T
         tp, mv, w = templates[t0:t0 + n], moveouts[t0:t0 + n], weights[t0:t0 + n]
         rc = self.lib.bpmf_mf_run_dev(
             tp.data_ptr(), mv.data_ptr(), w.data_ptr(), data.data_ptr(), self.step, self.L, self.N, n, self.S,
             self.C, self.normalize, self.network_sum, self.precision, self.trace_ws.data_ptr(),
             self.trace_ws.numel(), self.template_ws.data_ptr(), self.template_ws.numel(),
-            self.cc[t0:t0 + n].data_ptr(), self.pitch, _stream_ptr())
+            self.cc[r0:r0 + n].data_ptr(), self.pitch, _stream_ptr())
         _lib.check(rc, "mf_run_dev")
         self.last_precision = int(self.lib.bpmf_mf_last_precision())
 
@@ -230,3 +232,64 @@ def detect_dev(series, gaussian_sample, num_dev, half_window_samp, shift_samp, s
     v_, t_ = o_value[:k].cpu().numpy(), o_thr[:k].cpu().numpy()
     order = np.lexsort((i_, s_))
     return s_[order], i_[order], v_[order], t_[order]
+
+
+class DetectBatches:
+    """Threshold + declustering + compaction of many CC batches without a host synchronisation in between:
+    every batch gets its own counter and output region, the candidates are read back once (``collect``).
+
+    What replaces, for a template-sharded day, the per-template ``time_dependent_threshold`` /
+    ``select_cc_indexes`` calls of BPMF/similarity_search.py:548-666 when the CC slab stays on the device."""
+
+    def __init__(self, n_batches, n_series_per_batch, n, half_window_samp, shift_samp, capacity=1 << 18, device=None):
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_batches, self.B, self.n = int(n_batches), int(n_series_per_batch), int(n)
+        self.half, self.shift, self.capacity = int(half_window_samp), int(shift_samp), int(capacity)
+        ws = int(self.lib.bpmf_threshold_workspace_bytes(self.B, self.n, self.half, self.shift))
+        self.workspace = torch.empty(max(ws, 256), dtype=torch.uint8, device=self.device)
+        self.count = torch.zeros(self.n_batches, dtype=torch.int32, device=self.device)
+        self.series = torch.empty((self.n_batches, self.capacity), dtype=torch.int32, device=self.device)
+        self.index = torch.empty((self.n_batches, self.capacity), dtype=torch.int32, device=self.device)
+        self.value = torch.empty((self.n_batches, self.capacity), dtype=torch.float32, device=self.device)
+        self.thr = torch.empty((self.n_batches, self.capacity), dtype=torch.float32, device=self.device)
+
+    def run(self, k, series, gaussian_sample, num_dev, search_win=0, mode="select"):
+        """Enqueue the detection of batch ``k`` on ``series`` (B' <= B rows of a (.., pitch) device slab)."""
+        assert series.is_cuda and series.dtype == torch.float32 and series.dim() == 2 and series.stride(1) == 1
+        assert series.shape[0] <= self.B and 0 <= k < self.n_batches
+        g = _chk(gaussian_sample, torch.float32, "gaussian_sample")
+        rc = self.lib.bpmf_detect_dev(series.data_ptr(), series.stride(0), series.shape[0], g.data_ptr(), float(num_dev),
+                                      self.n, self.half, self.shift, int(search_win), 1 if mode == "select" else 0,
+                                      self.workspace.data_ptr(), self.workspace.numel(), self.count[k:].data_ptr(),
+                                      self.series[k].data_ptr(), self.index[k].data_ptr(), self.value[k].data_ptr(),
+                                      self.thr[k].data_ptr(), self.capacity, _stream_ptr())
+        _lib.check(rc, "detect_dev")
+
+    def packed(self):
+        """Device tensors (count (n_batches,), series, index, value, thr (n_batches, capacity)); no sync."""
+        return self.count, self.series, self.index, self.value, self.thr
+
+    def collect(self, series_offsets=None):
+        """Synchronise and return numpy (series, index, value, threshold) of every batch, series numbered
+        ``series_offsets[k] + local row`` (default k * B), sorted by (series, index)."""
+        import numpy as np
+
+        counts = self.count.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        if (counts > self.capacity).any():
+            raise _lib.BpmfError("DetectBatches: %d candidates exceed capacity %d" % (int(counts.max()), self.capacity))
+        out = [[], [], [], []]
+        for k, c in enumerate(counts):
+            c = int(c)
+            if c == 0:
+                continue
+            off = k * self.B if series_offsets is None else int(series_offsets[k])
+            out[0].append(self.series[k, :c].cpu().numpy().astype(np.int64) + off)
+            out[1].append(self.index[k, :c].cpu().numpy())
+            out[2].append(self.value[k, :c].cpu().numpy())
+            out[3].append(self.thr[k, :c].cpu().numpy())
+        if not out[0]:
+            return (np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.float32))
+        s_, i_, v_, t_ = (np.concatenate(x) for x in out)
+        order = np.lexsort((i_, s_))
+        return s_[order], i_[order], v_[order], t_[order]

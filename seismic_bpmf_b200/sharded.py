@@ -128,6 +128,91 @@ def matched_filter_sharded(templates, moveouts, weights, data, step=1, normalize
     return out
 
 
+def gather_detections(series, index, value, thr, group=None, device=None):
+    """All-gather of per-rank detection lists (numpy arrays of equal length per rank, GLOBAL series ids):
+    one collective for the counts, one for the padded records.  Returns the concatenation sorted by
+    (series, index) -- a few bytes per detection instead of the (T, n_corr) CC slab."""
+    import numpy as np
+
+    rank, world = _world(group)
+    if world == 1:
+        order = np.lexsort((index, series))
+        return series[order], index[order], value[order], thr[order]
+    device = torch.device("cpu") if device is None else device
+    n = torch.tensor([len(series)], dtype=torch.int64, device=device)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = counts.cpu().numpy()
+    m = int(counts.max())
+    if m == 0:
+        z = np.zeros(0)
+        return z.astype(np.int64), z.astype(np.int32), z.astype(np.float32), z.astype(np.float32)
+    # one (m, 4) float64 record per rank: series and index are exact in float64
+    rec = np.zeros((m, 4), dtype=np.float64)
+    rec[: len(series), 0], rec[: len(series), 1] = series, index
+    rec[: len(series), 2], rec[: len(series), 3] = value, thr
+    mine = torch.from_numpy(rec).to(device)
+    everyone = torch.empty((world, m, 4), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(everyone.view(-1), mine.view(-1), group=group)
+    everyone = everyone.cpu().numpy()
+    rows = np.concatenate([everyone[r, : counts[r]] for r in range(world)], axis=0)
+    order = np.lexsort((rows[:, 1], rows[:, 0]))
+    rows = rows[order]
+    return (rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int32), rows[:, 2].astype(np.float32),
+            rows[:, 3].astype(np.float32))
+
+
+def matched_filter_detect_sharded(templates, moveouts, weights, data, gaussian_sample, num_dev, window_samp,
+                                  overlap=0.25, search_win=0, step=1, normalize="short", precision="auto", group=None,
+                                  batch=64, capacity=1 << 18, compute=None, detect=None):
+    """The multi-GPU detection path: every rank runs the matched filter on its block of templates, thresholds and
+    declusters ITS OWN CC rows on the device (rms threshold of BPMF/libc.c:516-673 with ``half_window =
+    window_samp // 2``, ``shift = int((1 - overlap) * window_samp)`` as BPMF/clib.py:296-297, then
+    ``select_cc_indexes`` with ``search_win``), and only the detections are all-gathered.  The CC slab never
+    leaves the GPU that made it and is never held for more than ``batch`` templates at a time, so
+    BASELINE.json configs[3] (172.8 GB of CC) needs no more memory than one batch.
+
+    Returns numpy ``(template, index, cc, threshold)`` sorted by (template, index), identical on every rank.
+    ``compute`` / ``detect`` are injectable for the CPU (gloo) tests: ``compute`` as in matched_filter_sharded,
+    ``detect(local_cc) -> (row, index, cc, threshold)``."""
+    import numpy as np
+
+    rank, world = _world(group)
+    T, S, C, L = templates.shape
+    lo, hi = shard_bounds(T, rank, world)
+    half, shift = int(window_samp) // 2, int((1.0 - overlap) * int(window_samp))
+    if compute is not None or detect is not None:
+        assert compute is not None and detect is not None
+        if hi > lo:
+            local = compute(templates[lo:hi].contiguous(), moveouts[lo:hi].contiguous(), weights[lo:hi].contiguous(),
+                            data, step, normalize, precision)
+            s_, i_, v_, t_ = detect(local)
+        else:
+            s_, i_, v_, t_ = (np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32),
+                              np.zeros(0, np.float32))
+        return gather_detections(np.asarray(s_, np.int64) + lo, i_, v_, t_, group, data.device)
+    from . import device as dev
+
+    n_local = hi - lo
+    if n_local > 0:
+        batch = max(1, min(int(batch), n_local))
+        plan = dev.MatchedFilterPlan(batch, S, C, L, data.shape[-1], step=step, normalize=normalize,
+                                     precision=precision, device=data.device, batch=batch)
+        n_batches = (n_local + batch - 1) // batch
+        det = dev.DetectBatches(n_batches, batch, plan.n_corr, half, shift, capacity=capacity, device=data.device)
+        tp, mv, w = templates[lo:hi].contiguous(), moveouts[lo:hi].contiguous(), weights[lo:hi].contiguous()
+        plan.prepare(data)
+        for k, t0 in enumerate(range(0, n_local, batch)):
+            n_here = min(batch, n_local - t0)
+            plan.run_batch(tp, mv, w, data, t0, n_here, cc_row0=0)
+            det.run(k, plan.cc[:n_here], gaussian_sample, num_dev, search_win=search_win, mode="select")
+        s_, i_, v_, t_ = det.collect(series_offsets=[lo + k * batch for k in range(n_batches)])
+    else:
+        s_, i_, v_, t_ = (np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32),
+                          np.zeros(0, np.float32))
+    return gather_detections(s_, i_, v_, t_, group, data.device)
+
+
 def merge_max_argmax(maxes, args):
     """(G,N) per-shard maxima and GLOBAL source ids -> (N,), (N,) with ties to the lowest id."""
     best = maxes.max(dim=0).values

@@ -97,3 +97,47 @@ def test_find_similar_sources_multi_block():
         want = libc_numpy.find_similar_moveouts(tt, lon, lat, cl, cl, 0.3, nfd, variant).astype(bool)
         assert np.array_equal(got, want)
         assert 0 < got.sum() < K
+
+
+def test_threshold_is_reentrant_from_a_thread_pool(golden):
+    """BPMF calls time_dependent_threshold from a ThreadPoolExecutor with the GIL released
+    (BPMF/similarity_search.py:590-593): 8 threads x 6 calls each on the three golden series, concurrently with
+    select_cc_indexes calls, must all reproduce the reference's vectors."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    wn = golden["thr_white_noise"]
+
+    def one(k):
+        tag = "abc"[k % 3]
+        win, ov, nd = golden[f"thr_{tag}_params"]
+        thr = clib.time_dependent_threshold(golden[f"thr_{tag}_x"], int(win), float(nd), overlap=float(ov),
+                                            white_noise=wn, num_threads=1)
+        err = float(np.abs(thr - golden[f"thr_{tag}_out"]).max())
+        sel = clib.select_cc_indexes(golden[f"sel_{tag}_cc"], golden[f"sel_{tag}_thr"], int(golden[f"sel_{tag}_win"][0]))
+        return err, bool(np.array_equal(sel, golden[f"sel_{tag}_out"]))
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        results = list(pool.map(one, range(48)))
+    assert max(r[0] for r in results) < 2e-6
+    assert all(r[1] for r in results)
+
+
+def test_matched_filter_host_call_is_reentrant():
+    """Two threads inside fast_matched_filter.matched_filter at once (the second one finds the per-device buffer
+    cache busy and takes private buffers, csrc/abi.cu): both results equal the single-threaded ones."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import cpu
+    from seismic_bpmf_b200 import fast_matched_filter as fmf
+    from tests import _synth
+
+    cases = [_synth.mf_case(9, 4, 3, 200, 40000, seed=s) for s in (1, 2, 3, 4)]
+    want = [cpu.matched_filter(tp, mv, w, d, 1) for tp, mv, w, d, _ in cases]
+
+    def one(k):
+        tp, mv, w, d, _ = cases[k % 4]
+        return float(np.abs(fmf.matched_filter(tp, mv, w, d, 1, precision="fp32", check_zeros=False) - want[k % 4]).max())
+
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        errs = list(pool.map(one, range(16)))
+    assert max(errs) < 2e-6

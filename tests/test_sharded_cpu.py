@@ -74,7 +74,33 @@ def _worker(rank, world, port, ret):
                                               torch.from_numpy(ws), compute=beam_compute)
         mb_w, am_w = cpu.beamform(f, tau, wp, ws)
         ok_beam = np.array_equal(mb.numpy(), mb_w) and np.array_equal(am.numpy(), am_w)
-        ret[rank] = (ok_mf, ok_local, ok_beam)
+        # ---- shard-local detection + all-gather of the detections: 5 templates over 2 ranks
+        from oracle import libc_numpy
+
+        wn = np.random.default_rng(3).standard_normal(500).astype(np.float32)
+        tp3, mv3, w3, d3, planted = _synth.mf_case(5, 3, 2, 40, 6000, seed=14)
+
+        def mf1(t, m, ww, dd, step, normalize, precision):
+            return torch.from_numpy(cpu.matched_filter(t.numpy(), m.numpy(), ww.numpy(), dd.numpy(), step))
+
+        def detect(local):
+            rows, idx, val, thr = [], [], [], []
+            for r, cc in enumerate(local.numpy()):
+                th, _ = libc_numpy.time_dependent_threshold(cc, wn, 6.0, 1000 // 2, int(0.75 * 1000))
+                sel = libc_numpy.select_cc_indexes(cc, th, 50)
+                k = np.flatnonzero(sel)
+                rows.append(np.full(len(k), r)); idx.append(k); val.append(cc[k]); thr.append(th[k])
+            return (np.concatenate(rows), np.concatenate(idx).astype(np.int32), np.concatenate(val),
+                    np.concatenate(thr))
+
+        args3 = [torch.from_numpy(a) for a in (tp3, mv3, w3, d3)]
+        s_, i_, v_, t_ = sharded.matched_filter_detect_sharded(*args3, torch.from_numpy(wn), 6.0, 1000, overlap=0.25,
+                                                              search_win=50, compute=mf1, detect=detect)
+        ws_, wi_, wv_, wt_ = detect(mf1(*args3, 1, "short", "auto"))  # the same on one rank, all templates
+        order = np.lexsort((wi_, ws_))
+        ok_det = (np.array_equal(s_, ws_[order]) and np.array_equal(i_, wi_[order]) and np.array_equal(v_, wv_[order])
+                  and all(((s_ == t) & (i_ == i0)).any() for t, i0 in planted.items()))
+        ret[rank] = (ok_mf, ok_local, ok_beam and ok_det)
     finally:
         dist.destroy_process_group()
 
