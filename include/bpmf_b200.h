@@ -41,6 +41,8 @@ extern "C" {
 #define BPMF_MF_FP32 1       /* direct form on FP32 CUDA cores (exact-grade, ~1e-6) */
 #define BPMF_MF_TC_FP16 2    /* tcgen05, fp16 operands (power-of-two pre-scaled), fp32 accumulate */
 #define BPMF_MF_TC_FP16X3 3  /* tcgen05, hi/lo split of both operands (3 MMAs), fp32-grade */
+#define BPMF_MF_TC_MIXED 4   /* reported only (bpmf_mf_last_precision): AUTO ran FP16 for the templates whose
+                                weights allow it and FP16X3 for the others */
 
 const char *bpmf_last_error(void);
 /* The reference-named symbols of group (1) return void (BPMF/libc.h:1-11) and can only report a
@@ -129,11 +131,11 @@ void bpmf_release_cache(void);
 
 /* Shape-only check of a precision selector: returns the arithmetic it maps to, or a negative value
  * when it is not available for the shape.  For BPMF_MF_AUTO this is the fastest arithmetic the
- * shape allows; the call itself inspects the weights (4 bytes read back, the one host
- * synchronisation of bpmf_matched_filter_dev) and takes BPMF_MF_TC_FP16 only when the predicted
- * rounding error of the CC sum, 2.6e-3 * sqrt(max_t sum_ch w^2) / sqrt(L), is below 6e-5;
- * otherwise BPMF_MF_TC_FP16X3.  bpmf_mf_last_precision() reports what the calling thread's last
- * call used. */
+ * shape allows; the call itself classifies every TEMPLATE from its weights (8 bytes read back, the
+ * one host synchronisation of bpmf_matched_filter_dev): a template takes BPMF_MF_TC_FP16 when the
+ * predicted rounding error of its CC sum, 2.6e-3 * sqrt(sum_ch w^2) / sqrt(L), is below 6e-5,
+ * otherwise BPMF_MF_TC_FP16X3; a call with both kinds runs the two classes one after the other
+ * (BPMF_MF_TC_MIXED).  bpmf_mf_last_precision() reports what the calling thread's last call used. */
 int bpmf_mf_resolve_precision(size_t n_samples_template, size_t step, int normalize,
                               int network_sum, int precision);
 int bpmf_mf_last_precision(void);

@@ -12,7 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BPMF_B200_LIB") or os.path.join(HERE, "lib", "libbpmf_b200.so")
 
 OK = 0
-MF_AUTO, MF_FP32, MF_TC_FP16, MF_TC_FP16X3 = 0, 1, 2, 3
+MF_AUTO, MF_FP32, MF_TC_FP16, MF_TC_FP16X3, MF_TC_MIXED = 0, 1, 2, 3, 4
+PRECISION_NAMES = {MF_FP32: "fp32", MF_TC_FP16: "fp16", MF_TC_FP16X3: "fp16x3",
+                   MF_TC_MIXED: "fp16 / fp16x3 per template"}
 PRECISIONS = {"auto": MF_AUTO, "fp32": MF_FP32, "fp16": MF_TC_FP16, "tc": MF_TC_FP16,
               "fp16x3": MF_TC_FP16X3, "tc3": MF_TC_FP16X3}
 

@@ -23,6 +23,9 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static thread_local HostPool g_pool;
+HostPool &host_pool() { return g_pool; }
+
 static thread_local int g_status = 0;
 void set_status(int rc) { g_status = rc; }
 
@@ -107,8 +110,20 @@ static int resolve_precision(const MfShape &sh, int precision) {
     return precision;
 }
 
-// max over templates of sum_ch w^2 (one warp per template)
-__global__ void mf_weight_norm_kernel(const float *__restrict__ w, size_t T, size_t SC, float *__restrict__ out) {
+// AUTO on a tensor-capable shape, decided PER TEMPLATE: single-pass fp16 operands carry 2^-11 relative
+// rounding; a template's CC sum then errs by about 4e-4 * sqrt(sum_ch w^2) / sqrt(L) rms.  A template takes the
+// single pass when 6.5 sigma of that stays below 6e-5 (tolerance 1e-4 with margin), i.e. when
+// sum_ch w^2 < (6e-5 / 2.6e-3)^2 * L; otherwise the hi/lo split (fp32 grade).  One template with concentrated
+// weights therefore no longer drags a whole call of well-spread templates into the 3x slower arithmetic.
+__host__ __device__ inline float mf_auto_w2_limit(size_t L) {
+    const double r = 6e-5 / 2.6e-3;
+    return (float)(r * r * (double)L);
+}
+
+// one warp per template: sum_ch w^2 -> class; w_easy / w_hard are the weights with the other class zeroed
+__global__ void mf_weight_class_kernel(const float *__restrict__ w, size_t T, size_t SC, float w2_limit,
+                                       float *__restrict__ w_easy, float *__restrict__ w_hard,
+                                       unsigned *__restrict__ counts) {
     const size_t t = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= T) return;
     float a = 0.f;
@@ -118,26 +133,18 @@ __global__ void mf_weight_norm_kernel(const float *__restrict__ w, size_t T, siz
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(reinterpret_cast<unsigned *>(out), __float_as_uint(a));
+    const bool easy = a < w2_limit;
+    for (size_t c = threadIdx.x & 31; c < SC; c += 32) {
+        const float v = w[t * SC + c];
+        w_easy[t * SC + c] = easy ? v : 0.f;
+        w_hard[t * SC + c] = easy ? 0.f : v;
+    }
+    if ((threadIdx.x & 31) == 0 && a > 0.f) atomicAdd(counts + (easy ? 0 : 1), 1u);
 }
 
 static thread_local int g_last_precision = 0;
-static bool is_tc(int prec) { return prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3; }
-
-// AUTO on a tensor-capable shape: single-pass fp16 operands carry 2^-11 relative rounding; the CC
-// sum then errs by about 4e-4 * sqrt(sum_ch w^2) / sqrt(L) rms.  Take the single pass when 6.5
-// sigma of that stays below 6e-5 (tolerance 1e-4 with margin), else the hi/lo split (fp32 grade).
-static int mf_auto_precision(const MfShape &sh, const float *d_weights, float *d_scratch, cudaStream_t st,
-                             int *out) {
-    BPMF_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(float), st));
-    mf_weight_norm_kernel<<<(unsigned)((sh.T + 7) / 8), 256, 0, st>>>(d_weights, sh.T, sh.SC(), d_scratch);
-    BPMF_LAUNCH_CHECK();
-    float w2 = 0.f;
-    BPMF_CUDA(cudaMemcpyAsync(&w2, d_scratch, sizeof(float), cudaMemcpyDeviceToHost, st));
-    BPMF_CUDA(cudaStreamSynchronize(st));
-    const double predicted = 2.6e-3 * sqrt((double)w2) / sqrt((double)sh.L);
-    *out = (predicted < 6e-5) ? BPMF_MF_TC_FP16 : BPMF_MF_TC_FP16X3;
-    return BPMF_OK;
+static bool is_tc(int prec) {
+    return prec == BPMF_MF_TC_FP16 || prec == BPMF_MF_TC_FP16X3 || prec == BPMF_MF_TC_MIXED;
 }
 
 }  // namespace bpmf
@@ -230,6 +237,10 @@ extern "C" size_t bpmf_mf_template_workspace_bytes(size_t L, size_t N, size_t T,
     ws.take<float>(64);  // scratch of the AUTO policy
     carve_meta(ws, sh);
     if (is_tc(prec)) {
+        if (precision == BPMF_MF_AUTO) {  // per-template class: the two masked copies of the weights
+            ws.take<float>(sh.T * sh.SC());
+            ws.take<float>(sh.T * sh.SC());
+        }
         size_t need = mf_tc_template_ws_bytes(sh, prec == BPMF_MF_TC_FP16X3);
         if (precision == BPMF_MF_AUTO) need = std::max(need, mf_tc_template_ws_bytes(sh, 1));
         return ws.used + need;
@@ -287,15 +298,44 @@ extern "C" int bpmf_mf_run_dev(const float *d_templates, const int *d_moveouts, 
     BPMF_REQUIRE(pws.ok(), "matched_filter: template workspace too small");
     int rc;
     if (precision == BPMF_MF_AUTO && prec == BPMF_MF_TC_FP16) {
-        // the only host synchronisation of this entry point: 4 bytes of weight statistics
-        if ((rc = mf_auto_precision(sh, d_weights, scratch, st, &prec)) != BPMF_OK) return rc;
+        // classify every template on the device; the only host synchronisation of this entry point reads back
+        // the two class counts (8 bytes)
+        float *w_easy = pws.take<float>(sh.T * sh.SC());
+        float *w_hard = pws.take<float>(sh.T * sh.SC());
+        BPMF_REQUIRE(pws.ok(), "matched_filter: template workspace too small");
+        unsigned *counts = reinterpret_cast<unsigned *>(scratch);
+        BPMF_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned), st));
+        mf_weight_class_kernel<<<(unsigned)((sh.T + 7) / 8), 256, 0, st>>>(d_weights, sh.T, sh.SC(),
+                                                                         mf_auto_w2_limit(sh.L), w_easy, w_hard, counts);
+        BPMF_LAUNCH_CHECK();
+        unsigned h_counts[2] = {0, 0};
+        BPMF_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+        BPMF_CUDA(cudaStreamSynchronize(st));
+        if (h_counts[1] == 0) prec = BPMF_MF_TC_FP16;
+        else if (h_counts[0] == 0) prec = BPMF_MF_TC_FP16X3;
+        else {
+            // both classes present: the single pass over the well-spread templates, then the split over the
+            // others, accumulating into the same slab (each template row is touched by exactly one of them;
+            // tiles without a weighted template of the class are skipped by the kernel)
+            g_last_precision = BPMF_MF_TC_MIXED;
+            if ((rc = mf_prepass(sh, d_templates, d_moveouts, w_easy, d_data, meta, nullptr, nullptr, st)) != BPMF_OK)
+                return rc;
+            Workspace p1 = pws;
+            if ((rc = mf_tc_run(sh, 0, d_templates, d_moveouts, w_easy, meta, tws, true, p1, d_cc, cc_pitch, true,
+                                st)) != BPMF_OK)
+                return rc;
+            if ((rc = mf_prepass(sh, d_templates, d_moveouts, w_hard, d_data, meta, nullptr, nullptr, st)) != BPMF_OK)
+                return rc;
+            Workspace p2 = pws, t2(d_trace_ws, trace_ws_bytes);
+            return mf_tc_run(sh, 1, d_templates, d_moveouts, w_hard, meta, t2, true, p2, d_cc, cc_pitch, false, st);
+        }
     }
     g_last_precision = prec;
     if ((rc = mf_prepass(sh, d_templates, d_moveouts, d_weights, d_data, meta, nullptr, nullptr, st)) != BPMF_OK)
         return rc;
     if (is_tc(prec))
         return mf_tc_run(sh, prec == BPMF_MF_TC_FP16X3, d_templates, d_moveouts, d_weights, meta, tws,
-                         wants_lo(precision), pws, d_cc, cc_pitch, st);
+                         wants_lo(precision), pws, d_cc, cc_pitch, true, st);
     MfTraceWs w = carve_fp32_traces(tws, sh);
     BPMF_REQUIRE(tws.ok(), "matched_filter: trace workspace too small");
     if (!sh.network_sum) BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * sh.n_corr * sh.SC(), st));
@@ -357,6 +397,7 @@ static void cache_release(HostCache &c) {
 }  // namespace bpmf
 
 extern "C" void bpmf_release_cache(void) {
+    host_pool().release();  // the calling thread's libc scratch
     std::lock_guard<std::mutex> lk(g_cache_mu);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return;
@@ -378,21 +419,23 @@ extern "C" int bpmf_matched_filter(const float *templates, const int *moveouts, 
     const size_t pitch = network_sum ? align_up(n_corr, 64) : 0;
     const size_t row_elems = network_sum ? pitch : n_corr * SC;
 
-    // AUTO is resolved once, on the host copy of the weights (same rule as mf_auto_precision), so that the
-    // chunk loop below never synchronises
+    // AUTO is resolved per template (same rule as mf_weight_class_kernel), on the host copy of the weights: when every
+    // template falls in one class the chunk loop below never synchronises; a mixed set keeps AUTO and lets the
+    // device entry point run the two classes separately (8 bytes read back per chunk)
     if (precision == BPMF_MF_AUTO) {
         MfShape sh0 = make_shape(L, N, 1, S, C, step, normalize ? 1 : 0, network_sum ? 1 : 0);
         if (resolve_precision(sh0, precision) == BPMF_MF_TC_FP16) {
-            double w2max = 0.0;
+            const double lim = (double)mf_auto_w2_limit(L);
+            size_t n_easy = 0, n_hard = 0;
             for (size_t t = 0; t < T; t++) {
-                double a = 0.0;
-                for (size_t q = 0; q < SC; q++) a += (double)weights[t * SC + q] * (double)weights[t * SC + q];
-                w2max = std::max(w2max, a);
+                float a = 0.f;
+                for (size_t q = 0; q < SC; q++) a = fmaf(weights[t * SC + q], weights[t * SC + q], a);
+                if (a > 0.f) ((double)a < lim ? n_easy : n_hard)++;
             }
-            precision = (2.6e-3 * sqrt(w2max) / sqrt((double)L) < 6e-5) ? BPMF_MF_TC_FP16 : BPMF_MF_TC_FP16X3;
+            if (n_hard == 0) precision = BPMF_MF_TC_FP16;
+            else if (n_easy == 0) precision = BPMF_MF_TC_FP16X3;
         }
     }
-
 
     int dev = 0;
     BPMF_CUDA(cudaGetDevice(&dev));

@@ -80,6 +80,49 @@ struct DevBuf {
     T *as() const { return (T *)p; }
 };
 
+// Per-thread device scratch of the host-pointer libc entry points: one grow-only allocation and one stream per
+// calling thread, reused across calls.  BPMF calls these symbols hundreds of times per day of data, from a thread
+// pool (BPMF/similarity_search.py:590-593); cudaMalloc / cudaFree / stream creation per call cost more than the
+// kernels themselves (and cudaFree synchronises the whole device, serialising the pool's threads).
+struct HostPool {
+    cudaStream_t st = nullptr;
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    int dev = -1;
+    cudaError_t begin(size_t total_bytes) {
+        int d = 0;
+        cudaError_t e = cudaGetDevice(&d);
+        if (e != cudaSuccess) return e;
+        if (d != dev) { release(); dev = d; }
+        if (!st && (e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        total_bytes += 4096;
+        if (cap < total_bytes) {
+            if (base) cudaFree(base);
+            base = nullptr;
+            cap = 0;
+            if ((e = cudaMalloc((void **)&base, total_bytes + total_bytes / 4)) != cudaSuccess) return e;
+            cap = total_bytes + total_bytes / 4;
+        }
+        used = 0;
+        return cudaSuccess;
+    }
+    template <typename T>
+    T *take(size_t count) {
+        T *r = (T *)(base + used);
+        used += align_up(count * sizeof(T), 256);
+        return r;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        if (st) cudaStreamDestroy(st);
+        base = nullptr;
+        st = nullptr;
+        cap = used = 0;
+    }
+    // no destructor on purpose: at thread / process exit the CUDA context may already be gone
+};
+HostPool &host_pool();  // the calling thread's pool
+
 int num_sms();
 int reserved_sms();  // SMs the persistent kernels leave free (bpmf_set_reserved_sms)
 
@@ -118,6 +161,6 @@ int mf_tc_prepare_traces(const MfShape &sh, bool want_lo, const float *d_data, W
                          cudaStream_t st);
 int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int *d_moveouts,
               const float *d_weights, MfMeta meta, Workspace &trace_ws, bool traces_have_lo, Workspace &tpl_ws,
-              float *d_cc, size_t cc_pitch, cudaStream_t st);
+              float *d_cc, size_t cc_pitch, bool zero_cc, cudaStream_t st);
 
 }  // namespace bpmf

@@ -293,34 +293,25 @@ extern "C" int bpmf_detect_dev(const float *d_series, size_t pitch, size_t B, co
 }
 
 static int thr_host(float *x, float *gauss, float num_dev, size_t n, size_t half, size_t shift, float *thr) {
-    DevBuf dx, dg, dt, dws;
-    BPMF_CUDA(dx.alloc(sizeof(float) * n));
-    BPMF_CUDA(dg.alloc(sizeof(float) * GAUSS_LEN));
-    BPMF_CUDA(dt.alloc(sizeof(float) * n));
+    // the calling thread's own stream and scratch: called concurrently from a ThreadPoolExecutor
+    // (similarity_search.py:590)
     const size_t wsb = bpmf_threshold_workspace_bytes(1, n, half, shift);
-    BPMF_CUDA(dws.alloc(wsb));
-    cudaStream_t st;  // own stream: called concurrently from a ThreadPoolExecutor (similarity_search.py:590)
-    BPMF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    int rc = BPMF_OK;
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(dx.p, x, sizeof(float) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(dg.p, gauss, sizeof(float) * GAUSS_LEN, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
-        set_error("time_dependent_threshold: H2D -> %s", cudaGetErrorString(e));
-        rc = BPMF_E_CUDA;
+    HostPool &pool = host_pool();
+    BPMF_CUDA(pool.begin(2 * sizeof(float) * n + sizeof(float) * GAUSS_LEN + wsb + 4 * 256));
+    float *dx = pool.take<float>(n), *dt = pool.take<float>(n), *dg = pool.take<float>(GAUSS_LEN);
+    char *dws = pool.take<char>(wsb);
+    cudaStream_t st = pool.st;
+    BPMF_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(dg, gauss, sizeof(float) * GAUSS_LEN, cudaMemcpyHostToDevice, st));
+    int rc = bpmf_time_dependent_threshold_dev(dx, n, 1, dg, num_dev, n, half, shift, dws, wsb, dt, n, st);
+    if (rc != BPMF_OK) {
+        cudaStreamSynchronize(st);
+        return rc;
     }
-    if (rc == BPMF_OK)
-        rc = bpmf_time_dependent_threshold_dev(dx.as<float>(), n, 1, dg.as<float>(), num_dev, n, half,
-                                               shift, dws.p, wsb, dt.as<float>(), n, st);
-    if (rc == BPMF_OK) {
-        if ((e = cudaMemcpyAsync(thr, dt.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(x, dx.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-            (e = cudaStreamSynchronize(st)) != cudaSuccess) {
-            set_error("time_dependent_threshold: D2H -> %s", cudaGetErrorString(e));
-            rc = BPMF_E_CUDA;
-        }
-    }
-    cudaStreamDestroy(st);
-    return rc;
+    BPMF_CUDA(cudaMemcpyAsync(thr, dt, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    BPMF_CUDA(cudaMemcpyAsync(x, dx, sizeof(float) * n, cudaMemcpyDeviceToHost, st));  // zeros replaced, libc.c:606-612
+    BPMF_CUDA(cudaStreamSynchronize(st));
+    return BPMF_OK;
 }
 
 extern "C" void time_dependent_threshold(float *time_series, float *gaussian_sample, float num_dev,
@@ -361,16 +352,17 @@ __global__ void select_cc_kernel(const float *__restrict__ cc, const float *__re
 
 static int select_host(float *cc, float *thr, size_t W, size_t n, int *sel) {
     if (n == 0) return BPMF_OK;
-    DevBuf dc, dt, ds;
-    BPMF_CUDA(dc.alloc(sizeof(float) * n));
-    BPMF_CUDA(dt.alloc(sizeof(float) * n));
-    BPMF_CUDA(ds.alloc(sizeof(int) * n));
-    BPMF_CUDA(cudaMemcpy(dc.p, cc, sizeof(float) * n, cudaMemcpyHostToDevice));
-    BPMF_CUDA(cudaMemcpy(dt.p, thr, sizeof(float) * n, cudaMemcpyHostToDevice));
-    select_cc_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dc.as<float>(), dt.as<float>(), (long long)W,
-                                                          (long long)n, ds.as<int>());
+    HostPool &pool = host_pool();
+    BPMF_CUDA(pool.begin(2 * sizeof(float) * n + sizeof(int) * n + 3 * 256));
+    float *dc = pool.take<float>(n), *dt = pool.take<float>(n);
+    int *ds = pool.take<int>(n);
+    cudaStream_t st = pool.st;
+    BPMF_CUDA(cudaMemcpyAsync(dc, cc, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(dt, thr, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    select_cc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dc, dt, (long long)W, (long long)n, ds);
     BPMF_LAUNCH_CHECK();
-    BPMF_CUDA(cudaMemcpy(sel, ds.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    BPMF_CUDA(cudaMemcpyAsync(sel, ds, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    BPMF_CUDA(cudaStreamSynchronize(st));
     return BPMF_OK;
 }
 

@@ -69,6 +69,8 @@ struct TcParams {
     const int *row_e;        // (SC, MT, 128) delay folded into the A row: phase + moveout mod 8, in [0, 15)
     const float *row_scale;  // (SC, MT, 128) weight / (sA * sB * sqrt(sum T^2)), 0 = unused row
     const float *row_ithr;   // (SC, MT, 128) guard: contribute only where colinv < ithr
+    const int *row_t;        // (SC, MT, 128) template of the row, -1 = empty slot (tiles are formed PER CHANNEL from
+                             // the templates that weight it, so zero-weight (template, channel) pairs cost nothing)
     const int *item_active;  // (SC, MT)
     const int *lo, *hi;      // per template valid output range
     float *cc;
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 // row of phase 2pp of this thread's template in 16-lane half hh (lam = 16 hh + 4 a + pp)
                 const int row0 = quarter * 32 + 16 * hh + 4 * (lane >> 4) + pp;
                 const size_t mrow = (size_t)(ch * p.MT + mt) * TC_ROWS + row0;
-                const int t = mt * TC_TPL + 4 * quarter + 2 * hh + (lane >> 4);
+                const int t = p.row_t[mrow];
                 TcPair &r = pr[hh];
                 r.scale = p.row_scale[mrow];
                 r.ithr = p.row_ithr[mrow];
@@ -477,8 +479,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 r.ioff_out = 8 * (lane & 3) + 2 * pp;
                 r.lo = 1;
                 r.hi = 0;
-                if (t < p.T && r.scale != 0.f) { r.lo = p.lo[t]; r.hi = p.hi[t]; }
-                r.obase = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + r.ioff_out;
+                if (t >= 0 && r.scale != 0.f) { r.lo = p.lo[t]; r.hi = p.hi[t]; }
+                r.obase = p.cc + (size_t)(t >= 0 ? t : 0) * p.cc_pitch + r.ioff_out;
                 r.jj_full_lo = r.jj_any_lo = 1;
                 r.jj_full_hi = r.jj_any_hi = 0;
                 if (r.hi >= r.lo) {  // output of (column jj, phase ph) = 8 * (jj - q) + ph
@@ -542,10 +544,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
             const float ithr = p.row_ithr[mrow];
             const int q = p.row_q[mrow];
             const int e = p.row_e[mrow];  // in [0, 15)
-            const int t = mt * TC_TPL + (row >> 3);
+            const int t = p.row_t[mrow];
             const int ir = row & 7;
             int lo = 1, hi = 0;
-            if (t < p.T && scale != 0.f) { lo = p.lo[t]; hi = p.hi[t]; }
+            if (t >= 0 && scale != 0.f) { lo = p.lo[t]; hi = p.hi[t]; }
             // output index of column jj: i = 8 * (jj - q) + ir, valid iff lo <= i <= hi
             // <=> jj in [jj_lo, jj_hi]
             long long jj_lo = 1, jj_hi = 0;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
             }
             // after the transpose the lane still writes its own template: 16-byte pieces at
             // 8 * (lane & 3) + 4 * ((lane >> 2) & 1) floats into each 128-byte run
-            float *obase = p.cc + (size_t)(t < p.T ? t : 0) * p.cc_pitch + 8 * (lane & 3) + 4 * ((lane >> 2) & 1);
+            float *obase = p.cc + (size_t)(t >= 0 ? t : 0) * p.cc_pitch + 8 * (lane & 3) + 4 * ((lane >> 2) & 1);
             const bool b2 = (lane & 2) != 0, b1 = (lane & 1) != 0;
             const int t_begin = seg * p.seg_tiles;
             const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
@@ -645,6 +647,41 @@ __global__ void tc_data_convert_kernel(const float *__restrict__ data, size_t N,
     }
 }
 
+// Tiles are formed per channel: slot k of channel ch is the k-th template (in index order) that weights ch.
+// One CTA per channel, ballot prefix sums over the templates in chunks of 256.
+__global__ void __launch_bounds__(256)
+    tc_slot_kernel(const float *__restrict__ weights, const float *__restrict__ sst, const int *__restrict__ lo,
+                   const int *__restrict__ hi, int T, int SC, int n_slots, int *__restrict__ slot_t) {
+    __shared__ int warp_tot[8];
+    __shared__ int base_s;
+    const int ch = blockIdx.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    int *out = slot_t + (size_t)ch * n_slots;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += 256) {
+        const int t = t0 + tid;
+        bool used = false;
+        if (t < T) {
+            const float w = weights[(size_t)t * SC + ch], ss = sst[(size_t)t * SC + ch];
+            used = (w != 0.f) && (hi[t] >= lo[t]) && (ss > 0.f) && (ss < INFINITY);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, used);
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        int before = base_s;
+        for (int k = 0; k < wid; k++) before += warp_tot[k];
+        if (used) out[before + __popc(m & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int k = 0; k < 8; k++) tot += warp_tot[k];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+    for (int k = base_s + tid; k < n_slots; k += 256) out[k] = -1;
+}
+
 // One CTA per (template tile, channel), one thread per A row: builds the resident A images (one per
 // K chunk; hi then lo in split mode) in UMMA core-matrix order (K group c of 8 elements at
 // c*2048 + row*16 bytes) and the per-row epilogue constants.
@@ -653,21 +690,23 @@ __global__ void __launch_bounds__(TC_ROWS)
                             const float *__restrict__ weights, const float *__restrict__ sst,
                             const int *__restrict__ lo, const int *__restrict__ hi,
                             const float *__restrict__ ch_scale, int T, int SC, int L, int n_kc, int Kc, int split,
-                            int a_bytes, int a_img_bytes, uint8_t *__restrict__ aimg, int *__restrict__ row_q,
-                            int *__restrict__ row_e, float *__restrict__ row_scale, float *__restrict__ row_ithr,
+                            int a_bytes, int a_img_bytes, const int *__restrict__ slot_t,
+                            uint8_t *__restrict__ aimg, int *__restrict__ row_q, int *__restrict__ row_e,
+                            float *__restrict__ row_scale, float *__restrict__ row_ithr, int *__restrict__ row_t,
                             int *__restrict__ item_active, int debug, int epi) {
     const int mt = blockIdx.x, ch = blockIdx.y, MT = gridDim.x;
     const int row = threadIdx.x;
     int tl, ir;
     tc_row_decode(row, epi, tl, ir);
-    const int t = mt * TC_TPL + tl;
     const size_t item = (size_t)ch * MT + mt;
     const size_t mrow = item * TC_ROWS + row;
+    const int t = slot_t[item * TC_TPL + tl];  // -1: empty slot
+    row_t[mrow] = t;
 
     bool used = false;
     float w = 0.f, ss = 0.f;
     int m = 0;
-    if (t < T) {
+    if (t >= 0) {
         w = weights[(size_t)t * SC + ch];
         ss = sst[(size_t)t * SC + ch];
         m = moveouts[(size_t)t * SC + ch];
@@ -683,7 +722,7 @@ __global__ void __launch_bounds__(TC_ROWS)
     const int e = ir + (m - 8 * q0);
     int q = q0 + TC_FRONT / 8;  // staged traces start TC_FRONT samples early
     if (debug & 16) q &= ~3;    // triage only (wrong results): every 128-byte reduction run is line-aligned
-    const float *tp = templates + ((size_t)(t < T ? t : 0) * SC + ch) * (size_t)L;
+    const float *tp = templates + ((size_t)(t >= 0 ? t : 0) * SC + ch) * (size_t)L;
     float sA = 1.f;
     if (used) {
         float amax = 0.f;
@@ -762,7 +801,7 @@ static TcTraceWs tc_carve_traces(Workspace &ws, const MfShape &sh, const TcGeom 
 // template-side staging of one batch of T templates
 struct TcTplWs {
     uint8_t *aimg;
-    int *row_q, *row_e, *item_active;
+    int *row_q, *row_e, *row_t, *slot_t, *item_active;
     float *row_scale, *row_ithr;
     int MT;
 };
@@ -773,6 +812,8 @@ static TcTplWs tc_carve_templates(Workspace &ws, const MfShape &sh, const TcGeom
     w.aimg = ws.take<uint8_t>(SC * (size_t)w.MT * g.n_kc * g.a_bytes);
     w.row_q = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
     w.row_e = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
+    w.row_t = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
+    w.slot_t = ws.take<int>(SC * (size_t)w.MT * TC_TPL);
     w.row_scale = ws.take<float>(SC * (size_t)w.MT * TC_ROWS);
     w.row_ithr = ws.take<float>(SC * (size_t)w.MT * TC_ROWS);
     w.item_active = ws.take<int>(SC * (size_t)w.MT);
@@ -827,7 +868,7 @@ int mf_tc_prepare_traces(const MfShape &sh, bool want_lo, const float *d_data, W
 
 int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int *d_moveouts,
               const float *d_weights, MfMeta meta, Workspace &trace_ws, bool traces_have_lo, Workspace &tpl_ws,
-              float *d_cc, size_t cc_pitch, cudaStream_t st) {
+              float *d_cc, size_t cc_pitch, bool zero_cc, cudaStream_t st) {
     BPMF_REQUIRE(mf_tc_supported(sh.L, sh.step, sh.normalize, sh.network_sum),
                  "matched filter: shape not supported by the tensor path");
     BPMF_REQUIRE(!split || traces_have_lo, "matched filter: traces were prepared without the lo part");
@@ -839,20 +880,24 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     BPMF_REQUIRE(g.smem_bytes <= TC_SMEM_LIMIT, "matched filter: tensor-path tile exceeds shared memory");
     const size_t SC = sh.SC();
 
-    // templates: resident A images + per-row constants
+    // templates: per-channel tiles of the templates that weight the channel, resident A images + per-row constants
+    tc_slot_kernel<<<(unsigned)SC, 256, 0, st>>>(d_weights, meta.sst, meta.lo, meta.hi, (int)sh.T, (int)SC,
+                                                 w.MT * TC_TPL, w.slot_t);
+    BPMF_LAUNCH_CHECK();
     tc_template_prep_kernel<<<dim3((unsigned)w.MT, (unsigned)SC), TC_ROWS, 0, st>>>(
         d_templates, d_moveouts, d_weights, meta.sst, meta.lo, meta.hi, tw.ch_scale, (int)sh.T, (int)SC, (int)sh.L,
-        g.n_kc, g.Kc, split, g.a_bytes, g.a_img_bytes, w.aimg, w.row_q, w.row_e, w.row_scale, w.row_ithr,
-        w.item_active, tc_debug_flags(), epi);
+        g.n_kc, g.Kc, split, g.a_bytes, g.a_img_bytes, w.slot_t, w.aimg, w.row_q, w.row_e, w.row_scale, w.row_ithr,
+        w.row_t, w.item_active, tc_debug_flags(), epi);
     BPMF_LAUNCH_CHECK();
-    // cc_sum is accumulated with reductions: start from zero (also the value of never-computed outputs)
-    BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * cc_pitch, st));
+    // cc_sum is accumulated with reductions: start from zero (also the value of never-computed outputs); the
+    // second pass of a mixed-precision call adds to what the first one left
+    if (zero_cc) BPMF_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(float) * sh.T * cc_pitch, st));
 
     TcParams p;
     p.dh = tw.dh; p.dh_lo = tw.dh_lo; p.dh_pitch = g.dh_pitch;
     p.colinv = tw.colinv; p.ci_pitch = g.ci_pitch;
     p.aimg = w.aimg;
-    p.row_q = w.row_q; p.row_e = w.row_e; p.row_scale = w.row_scale; p.row_ithr = w.row_ithr;
+    p.row_q = w.row_q; p.row_e = w.row_e; p.row_scale = w.row_scale; p.row_ithr = w.row_ithr; p.row_t = w.row_t;
     p.item_active = w.item_active;
     p.lo = meta.lo; p.hi = meta.hi;
     p.cc = d_cc; p.cc_pitch = cc_pitch;

@@ -105,16 +105,17 @@ def test_threshold_is_reentrant_from_a_thread_pool(golden):
     select_cc_indexes calls, must all reproduce the reference's vectors."""
     from concurrent.futures import ThreadPoolExecutor
 
-    wn = golden["thr_white_noise"]
+    g = {k: golden[k] for k in golden.files}  # NpzFile reads lazily and is not thread-safe: load everything first
+    wn = g["thr_white_noise"]
 
     def one(k):
         tag = "abc"[k % 3]
-        win, ov, nd = golden[f"thr_{tag}_params"]
-        thr = clib.time_dependent_threshold(golden[f"thr_{tag}_x"], int(win), float(nd), overlap=float(ov),
+        win, ov, nd = g[f"thr_{tag}_params"]
+        thr = clib.time_dependent_threshold(g[f"thr_{tag}_x"], int(win), float(nd), overlap=float(ov),
                                             white_noise=wn, num_threads=1)
-        err = float(np.abs(thr - golden[f"thr_{tag}_out"]).max())
-        sel = clib.select_cc_indexes(golden[f"sel_{tag}_cc"], golden[f"sel_{tag}_thr"], int(golden[f"sel_{tag}_win"][0]))
-        return err, bool(np.array_equal(sel, golden[f"sel_{tag}_out"]))
+        err = float(np.abs(thr - g[f"thr_{tag}_out"]).max())
+        sel = clib.select_cc_indexes(g[f"sel_{tag}_cc"], g[f"sel_{tag}_thr"], int(g[f"sel_{tag}_win"][0]))
+        return err, bool(np.array_equal(sel, g[f"sel_{tag}_out"]))
 
     with ThreadPoolExecutor(max_workers=8) as pool:
         results = list(pool.map(one, range(48)))
