@@ -44,9 +44,22 @@ def tile_templates(T, per_tile=3, tile=16, extra=()):
 def compare(cc_rows, want, tol=1e-4):
     """cc_rows, want: (n_templates, n_windows, win_len).  Returns the parity record."""
     diff = np.abs(cc_rows.astype(np.float64) - want.astype(np.float64))
-    z_got, z_want = cc_rows == 0.0, want == 0.0
     worst = np.unravel_index(int(diff.argmax()), diff.shape)
+    structural, chance = zero_pattern(cc_rows, want)
     return {"compared_outputs": int(diff.size), "max_abs_err_vs_oracle": float(diff.max()), "tolerance": tol,
-            "mean_abs_err": float(diff.mean()), "exact_zeros_in_oracle": int(z_want.sum()),
-            "zero_pattern_mismatches": int((z_got != z_want).sum()), "worst_at": [int(x) for x in worst],
-            "ok": bool(diff.max() < tol and not (z_got != z_want).any())}
+            "mean_abs_err": float(diff.mean()), "exact_zeros_in_oracle": int((want == 0.0).sum()),
+            "zero_pattern_mismatches": structural, "chance_zeros": chance, "worst_at": [int(x) for x in worst],
+            "ok": bool(diff.max() < tol and structural == 0)}
+
+
+def zero_pattern(got, want, noise=2e-5):
+    """BPMF reads an exact 0.0 in a CC series as "no data here" (similarity_search.py:615, libc.c:561,609), so the
+    zeros must coincide.  A float32 sum of ~48 terms of magnitude 1e-3 also lands EXACTLY on 0.0 by cancellation about
+    once per 1e8 outputs (measured: 14-19 of the 4.3e9 outputs of configs[1], at either end of the comparison), with
+    the other side within rounding noise of zero: those are counted apart (`chance`), everything else -- a zero
+    against a value beyond `noise` -- is a structural mismatch."""
+    z_got, z_want = got == 0.0, want == 0.0
+    mism = z_got != z_want
+    other = np.where(z_got, np.abs(want), np.abs(got))
+    structural = int((mism & (other > noise)).sum())
+    return structural, int(mism.sum()) - structural

@@ -203,6 +203,16 @@ def test_auto_policy_and_long_templates():
     got = fmf.matched_filter(tp, mv, w1, d, 1, check_zeros=False)
     assert lib.bpmf_mf_last_precision() == _lib.MF_TC_FP16X3
     assert np.abs(got - cpu.matched_filter(tp, mv, w1, d, 1)).max() < 1e-5
+    # both kinds in one call: AUTO decides per TEMPLATE -- the well-spread templates keep the single pass, the two
+    # concentrated ones get the split, all rows land in the same slab
+    wm = w.copy()
+    wm[1], wm[3] = w1[1], w1[3]
+    got = fmf.matched_filter(tp, mv, wm, d, 1, check_zeros=False)
+    assert lib.bpmf_mf_last_precision() == _lib.MF_TC_MIXED
+    want_m = cpu.matched_filter(tp, mv, wm, d, 1)
+    assert np.abs(got - want_m).max() < TOL
+    assert np.abs(got[[1, 3]] - want_m[[1, 3]]).max() < 1e-5
+    assert np.array_equal(got == 0, want_m == 0)
     for L in (810, 1500, 2049):
         tp, mv, w, d, _ = _synth.mf_case(3, 3, 2, L, 20000, seed=L)
         want = cpu.matched_filter(tp, mv, w, d, 1)
