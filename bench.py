@@ -114,8 +114,8 @@ def make_inputs_device(torch, T, S, Cc, L, N, seed, device):
 
 def measured_traffic(kernel, T, S, Cc, L, N):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this exact
-    configuration (profiles/r1_traffic.json); None when the configuration was not captured."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    configuration (profiles/r2_traffic.json); None when the configuration was not captured."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(path):
         return None
     for rec in json.load(open(path)):

@@ -279,6 +279,20 @@ int bpmf_detect_dev(const float *d_series, size_t pitch, size_t n_series, const 
                     unsigned *d_count, int *d_series_idx, int *d_index, float *d_value, float *d_thr_value,
                     size_t capacity, void *stream);
 
+/* ---------------------------------------------------------------- (2d) backprojection peak picking
+ * The index part of Beamformer.find_detections (BPMF/template_search.py:603-610): utils._detect_peaks(maxbeam,
+ * mpd=minimum_interevent_time) -- rising-edge local maxima, then suppression by decreasing height of every peak
+ * closer than mpd samples to a kept one (BPMF/utils.py:2292-2345) -- followed by maxbeam[peak] > threshold[peak]
+ * (threshold may be NULL: _detect_peaks alone).  Among exactly equal heights the later peak wins (the reference
+ * leaves that order to NumPy's unstable default sort).  The host form returns the peaks in increasing order; the
+ * device form writes them unsorted and d_count[0] = their number (> capacity means truncated). */
+size_t bpmf_detect_peaks_workspace_bytes(size_t n_samples);
+int bpmf_detect_peaks(const float *x, const float *threshold, size_t n_samples, size_t mpd, int *peaks,
+                      size_t capacity, size_t *n_peaks);
+int bpmf_detect_peaks_dev(const float *d_x, const float *d_threshold, size_t n_samples, size_t mpd,
+                          void *d_workspace, size_t workspace_bytes, int *d_peaks, size_t capacity,
+                          unsigned *d_count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

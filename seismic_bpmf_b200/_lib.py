@@ -67,6 +67,9 @@ _SIGNATURES = {
                                                   C.POINTER(C.c_double)]),
     "bpmf_moveouts_from_travel_times_dev": (C.c_int, [vp, C.c_int, z, z, z, C.c_double, C.c_double, C.c_int, vp, vp,
                                                       vp, vp]),
+    "bpmf_detect_peaks_workspace_bytes": (z, [z]),
+    "bpmf_detect_peaks": (C.c_int, [fp, fp, z, z, ip, z, C.POINTER(z)]),
+    "bpmf_detect_peaks_dev": (C.c_int, [vp, vp, z, z, vp, z, vp, z, vp, vp]),
     "bpmf_normalize_traces": (C.c_int, [fp, z, z, fp]),
     "bpmf_normalize_traces_dev": (C.c_int, [vp, z, z, vp, vp, vp]),
     "kurtosis": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),

@@ -18,7 +18,7 @@ OBJDIR = os.path.join(HERE, "csrc", "_obj")
 LIBNAME = "libbpmf_b200.so"
 FEATURES_LIBNAME = "libbpmf_b200_features.so"  # detection traces (cuFFT + CUB); never loaded by the hot path
 FEATURES_SOURCES = ["features.cu"]
-SOURCES = ["abi.cu", "mf_prepass.cu", "mf_fp32.cu", "mf_tc.cu", "beam.cu", "libc_gpu.cu", "intertp.cu", "moveouts.cu"]
+SOURCES = ["abi.cu", "mf_prepass.cu", "mf_fp32.cu", "mf_tc.cu", "beam.cu", "libc_gpu.cu", "intertp.cu", "moveouts.cu", "peaks.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -355,7 +355,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     if (warp == 0) {
         // ===================== producer: bulk copies of A images and trace slices ==================
         if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
+            // BPMF_TC_DEBUG bits 6/7 (tuning): trace slices with the default / evict_last policy instead of evict_first
+            const uint64_t pol_a = l2_policy_evict_first();
+            const uint64_t pol = (p.debug & 64) ? l2_policy_evict_normal()
+                                                : ((p.debug & 128) ? l2_policy_evict_last() : l2_policy_evict_first());
             uint32_t n_item = 0, n_tile = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const TcItem im = tc_decode(p, it);
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
                 const uint8_t *src = p.aimg + ((size_t)(ch * p.MT + mt) * p.n_kc + im.kc) * p.a_bytes;
                 for (int off = 0; off < p.a_bytes; off += 16384) {
                     const int n = (p.a_bytes - off < 16384) ? (p.a_bytes - off) : 16384;
-                    bulk_g2s(a_s + off, src + off, (uint32_t)n, a_full, pol);
+                    bulk_g2s(a_s + off, src + off, (uint32_t)n, a_full, pol_a);
                 }
                 n_item++;
                 const int t_begin = seg * p.seg_tiles;
@@ -427,7 +430,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     } else if (warp == TC_EPI_WARP0 + TC_EPI_WARPS) {
         // ===================== rsqrt(energy) producer: 32-column slices for the epilogue ===========
         if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
+            const uint64_t pol = (p.debug & 64) ? l2_policy_evict_normal()
+                                                : ((p.debug & 128) ? l2_policy_evict_last() : l2_policy_evict_first());
             uint32_t n_chunk = 0;  // per half: chunks issued so far
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const TcItem im = tc_decode(p, it);
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
         const int half = ((warp - TC_EPI_WARP0) >> 2) & 1; // which 128 columns of the tile
         const int sub = (warp - TC_EPI_WARP0) >> 3;        // which chunks of that half: sub, sub + TC_EPI_SUBS, ...
-        const uint64_t red_policy = l2_policy_evict_last();
+        const uint64_t red_policy = (p.debug & 256) ? l2_policy_evict_normal() : l2_policy_evict_last();
         const int pp = (lane >> 2) & 3;                    // phase pair of this thread: phases 2pp, 2pp + 1
         uint32_t n_tile = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {

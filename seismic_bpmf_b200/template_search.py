@@ -99,3 +99,40 @@ class MoveoutTable:
             dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
             self._cache[key] = torch.from_numpy(mv).to(dev)
         return self._cache[key]
+
+
+def detect_peaks(x, mpd=1, threshold=None):
+    """``utils._detect_peaks(x, mpd=mpd)`` with its defaults (BPMF/utils.py:2203-2352: rising edges, suppression of
+    peaks closer than ``mpd`` by decreasing height), optionally followed by ``x[peaks] > threshold[peaks]``
+    (template_search.py:606-610), on the GPU.  Returns the peak indexes, increasing, int64."""
+    lib = _lib.load()
+    _lib.require_device()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = x.size
+    thr = None
+    if threshold is not None:
+        thr = np.ascontiguousarray(np.broadcast_to(np.asarray(threshold, dtype=np.float32), x.shape))
+    cap = max(1, n // 2 + 1)
+    peaks = np.empty(cap, dtype=np.int32)
+    n_peaks = C.c_size_t(0)
+    fp = C.POINTER(C.c_float)
+    rc = lib.bpmf_detect_peaks(x.ctypes.data_as(fp), thr.ctypes.data_as(fp) if thr is not None else None, n, int(mpd),
+                               peaks.ctypes.data_as(C.POINTER(C.c_int)), cap, C.byref(n_peaks))
+    _lib.check(rc, "bpmf_detect_peaks")
+    return peaks[: n_peaks.value].astype(np.int64)
+
+
+def find_detections(maxbeam, maxbeam_sources, detection_threshold, minimum_interevent_time_samp):
+    """The peak selection of ``Beamformer.find_detections`` (BPMF/template_search.py:603-628): peaks of the composite
+    network response at least ``minimum_interevent_time_samp`` apart and above the time-dependent threshold (GPU),
+    then "keep the largest peak for grouped detection" and ``np.unique`` on the handful of survivors (host, the
+    reference's own statements).  Returns ``(peak_indexes, source_indexes)``."""
+    maxbeam = np.asarray(maxbeam)
+    mpd = int(minimum_interevent_time_samp)
+    peak_indexes = detect_peaks(maxbeam, mpd=mpd, threshold=detection_threshold)
+    for i in range(len(peak_indexes)):
+        idx = np.int32(np.arange(max(0, peak_indexes[i] - mpd / 2), min(peak_indexes[i] + mpd / 2, len(maxbeam))))
+        idx_to_update = np.where(peak_indexes == peak_indexes[i])[0]
+        peak_indexes[idx_to_update] = np.argmax(maxbeam[idx]) + idx[0]
+    peak_indexes = np.unique(peak_indexes)
+    return peak_indexes, np.asarray(maxbeam_sources)[peak_indexes]
