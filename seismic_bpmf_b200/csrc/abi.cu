@@ -30,7 +30,7 @@ static thread_local int g_status = 0;
 void set_status(int rc) { g_status = rc; }
 
 static std::atomic<int> g_timing{0};
-constexpr int TIMER_RING = 256;
+constexpr int TIMER_RING = 2048;
 static thread_local cudaEvent_t g_ev[TIMER_RING][2];
 static thread_local int g_ev_created = 0, g_ev_count = 0;
 

@@ -260,6 +260,45 @@ def beamform_max_sharded(features, moveouts, weights_phases, weights_sources, ou
     return merge_max_argmax(packed_m, packed_a)
 
 
+def _beam_full_compute_cuda(features, moveouts, weights_phases, weights_sources, out_of_bounds):
+    from . import device as dev
+
+    K, S, P = moveouts.shape
+    plan = dev.BeamformPlan(K, S, features.shape[1], P, features.shape[-1], device=features.device)
+    return plan.run_full(features, moveouts, weights_phases, weights_sources, out_of_bounds)
+
+
+def beamform_none_sharded(features, moveouts, weights_phases, weights_sources, out_of_bounds="strict", group=None,
+                          gather=True, compute=None):
+    """Source-sharded beamforming with ``reduce="none"`` (BPMF/template_search.py:560-569, consumed by
+    BPMF/dataset.py:2184-2196): rank r stacks the block ``[lo, hi)`` of the K sources; the (K/G, N) blocks are
+    concatenated in source order by one all-gather.  Returns the ``(K, N)`` beam on every rank
+    when ``gather`` is true, else ``(local_beam, (lo, hi))`` -- the K x N array of a large grid only fits sharded."""
+    rank, world = _world(group)
+    K, N = moveouts.shape[0], features.shape[-1]
+    lo, hi = shard_bounds(K, rank, world)
+    compute = compute or _beam_full_compute_cuda
+    if hi > lo:
+        local = compute(features, moveouts[lo:hi].contiguous(), weights_phases, weights_sources[lo:hi].contiguous(),
+                        out_of_bounds)
+    else:
+        local = torch.zeros((0, N), dtype=torch.float32, device=features.device)
+    if not gather:
+        return local, (lo, hi)
+    if world == 1:
+        return local
+    rows = (K + world - 1) // world  # equal-sized slabs for the collective: short shards are zero padded
+    slab = torch.zeros((rows, N), dtype=torch.float32, device=features.device)
+    slab[: hi - lo] = local
+    full = torch.empty((world * rows, N), dtype=torch.float32, device=features.device)
+    dist.all_gather_into_tensor(full.view(-1), slab.view(-1), group=group)
+    out = torch.empty((K, N), dtype=torch.float32, device=features.device)
+    for r in range(world):
+        a, b = shard_bounds(K, r, world)
+        out[a:b] = full[r * rows: r * rows + (b - a)]
+    return out
+
+
 class PeerSlabGather:
     """All-gather of equally sized float32 slabs through NVLink/NVSwitch peer memory, moved by the copy
     engines instead of SM kernels.

@@ -65,6 +65,12 @@ def _worker(rank, world, port, ret):
         ok_beam = float(np.abs(mb.cpu().numpy() - mb_w).max()) < 1e-5 and \
             np.array_equal(am.cpu().numpy()[clear], am_w[clear])
 
+        fullb = sharded.beamform_none_sharded(torch.from_numpy(f[:, :, :3000].copy()).to(dev),
+                                              torch.from_numpy(tau.astype(np.int32)).to(dev),
+                                              torch.from_numpy(wp).to(dev), torch.from_numpy(ws).to(dev))
+        ok_beam = ok_beam and float(np.abs(fullb.cpu().numpy() - cpu.beamform(f[:, :, :3000].copy(), tau, wp, ws,
+                                                                                reduce="none")).max()) < 1e-5
+
         # copy-engine peer gather: every rank ends with every rank's slab, batch after batch
         n = 5000
         g = sharded.PeerSlabGather(n, dev)

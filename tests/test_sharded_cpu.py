@@ -74,6 +74,15 @@ def _worker(rank, world, port, ret):
                                               torch.from_numpy(ws), compute=beam_compute)
         mb_w, am_w = cpu.beamform(f, tau, wp, ws)
         ok_beam = np.array_equal(mb.numpy(), mb_w) and np.array_equal(am.numpy(), am_w)
+
+        # reduce="none": the (K/G, N) blocks concatenated in source order (7 sources over 2 ranks: uneven shards)
+        def beam_full_compute(ff, tt, wpp, wss, oob):
+            return torch.from_numpy(cpu.beamform(ff.numpy(), tt.numpy(), wpp.numpy(), wss.numpy(), out_of_bounds=oob,
+                                                 reduce="none"))
+
+        full = sharded.beamform_none_sharded(torch.from_numpy(f), torch.from_numpy(tau), torch.from_numpy(wp),
+                                             torch.from_numpy(ws), compute=beam_full_compute)
+        ok_beam = ok_beam and np.array_equal(full.numpy(), cpu.beamform(f, tau, wp, ws, reduce="none"))
         # ---- shard-local detection + all-gather of the detections: 5 templates over 2 ranks
         from oracle import libc_numpy
 

@@ -52,7 +52,7 @@ def run(K=50000, N=432000, S=32, keep=32, random_moveouts=False, steps=3, warmup
         plan.run_max(feat, tau, wp, ws)
     torch.cuda.synchronize()
     lib.bpmf_set_kernel_timing(1)
-    lib.bpmf_main_kernel_times((C.c_float * 256)(), 256)  # drain earlier records
+    lib.bpmf_main_kernel_times((C.c_float * 2048)(), 2048)  # drain earlier records
     sampler = ClockSampler(device_index).start()
     t0 = time.perf_counter()
     for _ in range(steps):

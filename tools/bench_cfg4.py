@@ -139,15 +139,15 @@ def run(rank, world, device, steps=2, warmup=1, precision="auto", seed=20240726,
             step(mode)
         barrier()
         lib.bpmf_set_kernel_timing(1)
-        lib.bpmf_main_kernel_times((C.c_float * 256)(), 256)
+        lib.bpmf_main_kernel_times((C.c_float * 2048)(), 2048)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             step(mode)
         e1.record()
         barrier()
-        buf = (C.c_float * 256)()
-        nk = lib.bpmf_main_kernel_times(buf, 256)
+        buf = (C.c_float * 2048)()
+        nk = lib.bpmf_main_kernel_times(buf, 2048)
         lib.bpmf_set_kernel_timing(0)
         kernel_ms = sum(buf[i] for i in range(nk)) / steps if nk else None
         t = torch.tensor([e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
