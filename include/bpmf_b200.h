@@ -128,6 +128,12 @@ int bpmf_mf_run_dev(const float *d_templates, const int *d_moveouts, const float
                     void *stream);
 /* frees the device buffers the host-pointer entry points keep cached on the current device */
 void bpmf_release_cache(void);
+/* BPMF loops template chunks over one day of traces, one matched_filter call per chunk on the same `data` array
+ * (BPMF/similarity_search.py:773-790).  Between hold and release the caller promises that the host buffer at `data`
+ * does not change: bpmf_matched_filter then uploads and stages it once and reuses the device copy for every call
+ * that passes the same pointer and shape (same L, step, normalize, precision).  Nothing is cached without a hold. */
+int bpmf_mf_hold_traces(const float *data, size_t n_samples_data, size_t n_stations, size_t n_components);
+void bpmf_mf_release_traces(void);
 
 /* Shape-only check of a precision selector: returns the arithmetic it maps to, or a negative value
  * when it is not available for the shape.  For BPMF_MF_AUTO this is the fastest arithmetic the

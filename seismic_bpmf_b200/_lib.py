@@ -50,6 +50,8 @@ _SIGNATURES = {
     "bpmf_mf_run_dev": (C.c_int, [vp, vp, vp, vp, z, z, z, z, z, z, C.c_int, C.c_int, C.c_int, vp, z, vp, z,
                                   vp, z, vp]),
     "bpmf_release_cache": (None, []),
+    "bpmf_mf_hold_traces": (C.c_int, [fp, z, z, z]),
+    "bpmf_mf_release_traces": (None, []),
     "bpmf_mf_resolve_precision": (C.c_int, [z, z, C.c_int, C.c_int, C.c_int]),
     "bpmf_mf_last_precision": (C.c_int, []),
     "matched_filter": (None, [fp, fp, ip, fp, fp, z, z, z, z, z, z, z, C.c_int, fp]),

@@ -371,6 +371,13 @@ struct HostCache {
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t ev = nullptr;
     bool busy = false;
+    // bpmf_mf_hold_traces: the caller promises that this host buffer does not change until it is released, so the
+    // uploaded + staged copy (slots 0 and 1) can serve every call made on it meanwhile
+    const float *held_ptr = nullptr;
+    size_t held_N = 0, held_SC = 0;
+    bool staged = false;
+    size_t st_L = 0, st_step = 0;
+    int st_norm = 0, st_netsum = 0, st_prec = 0;
 };
 static HostCache g_cache[16];
 static std::mutex g_cache_mu;
@@ -402,6 +409,33 @@ extern "C" void bpmf_release_cache(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return;
     if (!g_cache[dev].busy) cache_release(g_cache[dev]);
+}
+
+// BPMF runs its template groups chunk by chunk over ONE day of traces (BPMF/similarity_search.py:773-790: every chunk
+// is a separate fast_matched_filter.matched_filter call on the same `data` array).  Between bpmf_mf_hold_traces and
+// bpmf_mf_release_traces the host entry point uploads and stages that array once and reuses it for every call that
+// passes the same pointer and shape, instead of moving 1.7-3.3 GB per chunk.  Explicit on purpose: a pointer can be
+// reused for the next day's samples, so nothing is cached unless the caller says the buffer is stable.
+extern "C" int bpmf_mf_hold_traces(const float *data, size_t N, size_t S, size_t C) {
+    int dev = 0;
+    BPMF_CUDA(cudaGetDevice(&dev));
+    BPMF_REQUIRE(dev >= 0 && dev < 16, "hold_traces: device index out of range");
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    HostCache &c = g_cache[dev];
+    BPMF_REQUIRE(!c.busy, "hold_traces: a matched-filter call is running on this device");
+    c.held_ptr = data;
+    c.held_N = N;
+    c.held_SC = S * C;
+    c.staged = false;
+    return BPMF_OK;
+}
+
+extern "C" void bpmf_mf_release_traces(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache[dev].held_ptr = nullptr;
+    g_cache[dev].staged = false;
 }
 
 // Traces go up and are staged once; templates are processed in chunks on two streams so the
@@ -510,10 +544,20 @@ extern "C" int bpmf_matched_filter(const float *templates, const int *moveouts, 
         MF_TRY(cache_get(*c, 2 + 5 * i + 3, sizeof(float) * Tc * row_elems, &d_cc[i]));
         MF_TRY(cache_get(*c, 2 + 5 * i + 4, tpl_b, &d_ws[i]));
     }
-    MF_TRY(cudaMemcpyAsync(d_data, data, sizeof(float) * SC * N, cudaMemcpyHostToDevice, c->st[0]));
-    rc = bpmf_mf_prepare_traces_dev((const float *)d_data, step, L, N, S, C, normalize, network_sum, precision,
-                                    d_trace, trace_b, c->st[0]);
-    if (rc != BPMF_OK) { cudaDeviceSynchronize(); return finish(rc); }
+    const bool held = cached && c->held_ptr == data && c->held_N == N && c->held_SC == SC;
+    const bool reuse = held && c->staged && c->st_L == L && c->st_step == step && c->st_norm == normalize &&
+                       c->st_netsum == network_sum && c->st_prec == precision;
+    if (!reuse) {
+        c->staged = false;
+        MF_TRY(cudaMemcpyAsync(d_data, data, sizeof(float) * SC * N, cudaMemcpyHostToDevice, c->st[0]));
+        rc = bpmf_mf_prepare_traces_dev((const float *)d_data, step, L, N, S, C, normalize, network_sum, precision,
+                                        d_trace, trace_b, c->st[0]);
+        if (rc != BPMF_OK) { cudaDeviceSynchronize(); return finish(rc); }
+        if (held) {
+            c->staged = true;
+            c->st_L = L; c->st_step = step; c->st_norm = normalize; c->st_netsum = network_sum; c->st_prec = precision;
+        }
+    }
     MF_TRY(cudaEventRecord(c->ev, c->st[0]));
 
     size_t chunk = 0;

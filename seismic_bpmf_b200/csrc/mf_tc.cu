@@ -41,7 +41,7 @@ constexpr int TC_TPL = 16;          // templates per tile
 constexpr int TC_NCOL = 256;        // GEMM columns per tile (= 2048 samples)
 constexpr int TC_KC_MAX = 816;      // resident A, single pass: 128 x 816 fp16 = 208 896 B
 constexpr int TC_KC_MAX_SPLIT = 384; // resident A, hi + lo images: 128 x 384 x 2 x 2 = 196 608 B
-constexpr int TC_SEG_TILES = 32;    // tiles swept per resident A image (65 536 samples)
+constexpr int TC_SEG_TILES = 64;    // tiles swept per resident A image (131 072 samples)
 #ifndef TC_EPI_WARPS
 #define TC_EPI_WARPS 16             // 8 or 16: with 16, two warps share each (lane quarter, tile half) and take alternate chunks
 #endif
@@ -355,10 +355,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     if (warp == 0) {
         // ===================== producer: bulk copies of A images and trace slices ==================
         if (lane == 0) {
-            // BPMF_TC_DEBUG bits 6/7 (tuning): trace slices with the default / evict_last policy instead of evict_first
+            // The A images are read once per item (evict first); the trace slices and rsqrt(energy) slices of a
+            // segment are read again by the next template tiles a fraction of a millisecond later: default policy
+            // (measured: 168 GB of DRAM traffic per configs[1] pass against 263 GB with evict_first, same run time).
+            // BPMF_TC_DEBUG bits 6/7 (tuning): evict_first / evict_last instead.
             const uint64_t pol_a = l2_policy_evict_first();
-            const uint64_t pol = (p.debug & 64) ? l2_policy_evict_normal()
-                                                : ((p.debug & 128) ? l2_policy_evict_last() : l2_policy_evict_first());
+            const uint64_t pol = (p.debug & 64) ? l2_policy_evict_first()
+                                                : ((p.debug & 128) ? l2_policy_evict_last() : l2_policy_evict_normal());
             uint32_t n_item = 0, n_tile = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const TcItem im = tc_decode(p, it);
@@ -430,8 +433,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     } else if (warp == TC_EPI_WARP0 + TC_EPI_WARPS) {
         // ===================== rsqrt(energy) producer: 32-column slices for the epilogue ===========
         if (lane == 0) {
-            const uint64_t pol = (p.debug & 64) ? l2_policy_evict_normal()
-                                                : ((p.debug & 128) ? l2_policy_evict_last() : l2_policy_evict_first());
+            const uint64_t pol = (p.debug & 64) ? l2_policy_evict_first()
+                                                : ((p.debug & 128) ? l2_policy_evict_last() : l2_policy_evict_normal());
             uint32_t n_chunk = 0;  // per half: chunks issued so far
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const TcItem im = tc_decode(p, it);
@@ -607,6 +610,331 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_kernel(const TcParams p) 
     }
 }
 
+// ---------------------------------------------------------------- the kernel, CTA pairs (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) work on the SAME channel and the SAME trace tiles with two different
+// template tiles: one tcgen05.mma.cta_group::2 of M = 256 covers both, each CTA keeping its own resident A image and
+// staging only HALF of the trace slice (128 of the 256 GEMM columns) -- the tensor cores of the pair read the two
+// halves from both shared memories.  Per CTA and K step the operand fetch drops from 4 KB (A) + 8 KB (B) to 4 + 4 KB:
+// the shared-memory data path, which the epilogue's loads and reductions share with the MMA operand fetch and which
+// the ncu capture of the one-CTA kernel shows as the co-limiter (profiles/r2_matched_filter_tc.md), gets a third of
+// its MMA load back.  Roles per CTA as in mf_tc_kernel; the MMA is issued by the even CTA only, the odd CTA's warp 1
+// relays "my A image / trace half has landed" to the leader's barriers; completion of the MMAs is multicast to the
+// barriers of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// Remote arrive with the default semantics (release at CTA scope), as CUTLASS's ClusterBarrier does: what crosses the
+// pair here is "an operand landed in shared memory" / "an accumulator was drained from tensor memory", consumed by
+// the tensor core's async proxy -- no global-memory ordering is implied.  (A .release.cluster arrive compiles to
+// MEMBAR.ALL.GPU, which made every epilogue warp wait for its own reductions to drain: measured 8 % slower.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint64_t *bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) mf_tc_pair_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *a_s = smem;
+    uint8_t *b_s = smem + p.a_bytes;
+    float *inv_s = reinterpret_cast<float *>(b_s + TC_NB * p.b_stage_bytes);  // [2 halves][TC_NI][TC_INV_SLOT]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(inv_s + 2 * TC_NI * TC_INV_SLOT);
+    uint64_t *a_full = bars + 0, *a_empty = bars + 1;
+    uint64_t *acc_full = bars + 2, *acc_empty = bars + 4;               // [2]
+    uint64_t *b_full = bars + 6, *b_empty = bars + 6 + TC_NB;           // [TC_NB]
+    uint64_t *inv_full = bars + 6 + 2 * TC_NB;                          // [2][TC_NI]
+    uint64_t *inv_empty = inv_full + 2 * TC_NI;                         // [2][TC_NI]
+    uint64_t *a_peer_full = inv_empty + 2 * TC_NI;                      // leader only: the odd CTA's A image landed
+    uint64_t *b_peer_full = a_peer_full + 1;                            // [TC_NB] leader only: its trace half landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_peer_full + TC_NB);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();           // 0 = leader (issues the MMAs), 1 = its pair
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        mbar_init(a_peer_full, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(acc_full + i, 1);
+            mbar_init(acc_empty + i, 2 * TC_EPI_WARPS);  // the epilogue warps of BOTH CTAs (used on the leader)
+        }
+        for (int i = 0; i < TC_NB; i++) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 1);
+            mbar_init(b_peer_full + i, 1);
+        }
+        for (int i = 0; i < 2 * TC_NI; i++) {
+            mbar_init(inv_full + i, 1);
+            mbar_init(inv_empty + i, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before anyone arrives remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int MTP = p.MT >> 1;  // template tile PAIRS (MT is even here)
+    const int n_items = p.n_seg * MTP * p.SC * p.n_kc;
+    const uint32_t b_bytes = (uint32_t)p.b_slice_bytes;  // (8*127 + Kc) * 2: this CTA's 128 columns
+
+    // item -> (kc, ch, tile pair, segment), same order as the one-CTA kernel
+    auto decode = [&](int it, int &kc, int &ch, int &mt, int &seg) {
+        kc = it % p.n_kc;
+        it /= p.n_kc;
+        ch = it % p.SC;
+        it /= p.SC;
+        mt = 2 * (it % MTP) + (int)rank;
+        seg = it / MTP;
+    };
+    auto pair_active = [&](int ch, int mt) {
+        return p.item_active[ch * p.MT + (mt & ~1)] | p.item_active[ch * p.MT + (mt | 1)];
+    };
+
+    if (warp == 0) {
+        // ===================== producer: this CTA's A image and its half of every trace slice ================
+        if (lane == 0) {
+            const uint64_t pol_a = l2_policy_evict_first(), pol = l2_policy_evict_normal();
+            uint32_t n_item = 0, n_tile = 0;
+            for (int it = cluster_id; it < n_items; it += n_clusters) {
+                int kc, ch, mt, seg;
+                decode(it, kc, ch, mt, seg);
+                if (!pair_active(ch, mt)) continue;
+                mbar_wait(a_empty, (n_item & 1) ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)p.a_bytes);
+                const uint8_t *src = p.aimg + ((size_t)(ch * p.MT + mt) * p.n_kc + kc) * p.a_bytes;
+                for (int off = 0; off < p.a_bytes; off += 16384) {
+                    const int n = (p.a_bytes - off < 16384) ? (p.a_bytes - off) : 16384;
+                    bulk_g2s(a_s + off, src + off, (uint32_t)n, a_full, pol_a);
+                }
+                n_item++;
+                const int t_begin = seg * p.seg_tiles;
+                const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+                for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
+                    const int s = n_tile % TC_NB;
+                    mbar_wait(b_empty + s, ((n_tile / TC_NB) & 1) ^ 1);
+                    const size_t d_off = (size_t)ch * p.dh_pitch + ((size_t)tile * TC_NCOL + 128 * rank) * 8 + (size_t)kc * p.Kc;
+                    mbar_expect_tx(b_full + s, p.split ? 2 * b_bytes : b_bytes);
+                    bulk_g2s(b_s + s * p.b_stage_bytes, p.dh + d_off, b_bytes, b_full + s, pol);
+                    if (p.split) bulk_g2s(b_s + s * p.b_stage_bytes + b_bytes, p.dh_lo + d_off, b_bytes, b_full + s, pol);
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 1) {
+        // ===================== relay (odd CTA): tell the leader when this CTA's operands have landed =========
+        if (lane == 0) {
+            const uint32_t a_peer = mapa_u32(smem_u32(a_peer_full), 0);
+            const uint32_t b_peer = mapa_u32(smem_u32(b_peer_full), 0);
+            uint32_t n_item = 0, n_tile = 0;
+            for (int it = cluster_id; it < n_items; it += n_clusters) {
+                int kc, ch, mt, seg;
+                decode(it, kc, ch, mt, seg);
+                if (!pair_active(ch, mt)) continue;
+                mbar_wait(a_full, n_item & 1);
+                mbar_arrive_cluster(a_peer);
+                n_item++;
+                const int t_begin = seg * p.seg_tiles;
+                const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+                for (int k = t_begin; k < t_end; k++, n_tile++) {
+                    const int s = n_tile % TC_NB;
+                    mbar_wait(b_full + s, (n_tile / TC_NB) & 1);
+                    mbar_arrive_cluster(b_peer + 8u * (uint32_t)s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread of the leader CTA, for the pair) ======================
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc(2 * TC_ROWS, TC_NCOL);
+            const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+            const int n_k = p.Kc / 16;
+            uint32_t n_item = 0, n_tile = 0;
+            for (int it = cluster_id; it < n_items; it += n_clusters) {
+                int kc, ch, mt, seg;
+                decode(it, kc, ch, mt, seg);
+                if (!pair_active(ch, mt)) continue;
+                mbar_wait(a_full, n_item & 1);
+                mbar_wait(a_peer_full, n_item & 1);
+                n_item++;
+                const int t_begin = seg * p.seg_tiles;
+                const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+                for (int k = t_begin; k < t_end; k++, n_tile++) {
+                    const int s = n_tile % TC_NB;
+                    const int sa = n_tile & 1;
+                    mbar_wait(b_full + s, (n_tile / TC_NB) & 1);
+                    mbar_wait(b_peer_full + s, (n_tile / TC_NB) & 1);
+                    mbar_wait(acc_empty + sa, ((n_tile >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(sa * TC_NCOL);
+                    for (int kk = 0; kk < n_k; kk++) {
+                        const uint64_t da = tc_desc(a_addr + (uint32_t)kk * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
+                        const uint32_t b_at = b_addr + (uint32_t)(s * p.b_stage_bytes) + (uint32_t)kk * 32;
+                        const uint64_t db = tc_desc(b_at, 16, 128);
+                        tc_mma2_f16(d_tmem, da, db, idesc, kk > 0 ? 1u : 0u);
+                        if (p.split) {
+                            const uint64_t db_lo = tc_desc(b_at + b_bytes, 16, 128);
+                            const uint64_t da_lo = tc_desc(a_addr + (uint32_t)p.a_img_bytes + (uint32_t)kk * 2 * (TC_ROWS * 16),
+                                                           TC_ROWS * 16, 128);
+                            tc_mma2_f16(d_tmem, da, db_lo, idesc, 1u);
+                            tc_mma2_f16(d_tmem, da_lo, db, idesc, 1u);
+                        }
+                    }
+                    tc_commit2(b_empty + s);    // both producers may overwrite their trace halves
+                    tc_commit2(acc_full + sa);  // both epilogues may read their accumulators
+                }
+                tc_commit2(a_empty);
+            }
+        }
+    } else if (warp == TC_EPI_WARP0 + TC_EPI_WARPS) {
+        // ===================== rsqrt(energy) producer (per CTA, as in the one-CTA kernel) ===================
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_normal();
+            uint32_t n_chunk = 0;
+            for (int it = cluster_id; it < n_items; it += n_clusters) {
+                int kc, ch, mt, seg;
+                decode(it, kc, ch, mt, seg);
+                if (!pair_active(ch, mt)) continue;
+                const int t_begin = seg * p.seg_tiles;
+                const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+                const float *ci = p.colinv + (size_t)ch * p.ci_pitch;
+                for (int tile = t_begin; tile < t_end; tile++) {
+                    for (int chunk = 0; chunk < 4; chunk++, n_chunk++) {
+                        const int slot = n_chunk % TC_NI;
+                        const uint32_t par = ((n_chunk / TC_NI) & 1) ^ 1;
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            uint64_t *full = inv_full + h * TC_NI + slot;
+                            mbar_wait(inv_empty + h * TC_NI + slot, par);
+                            mbar_expect_tx(full, TC_INV_SLOT * 4);
+                            bulk_g2s(inv_s + (h * TC_NI + slot) * TC_INV_SLOT,
+                                     ci + 8 * ((size_t)tile * TC_NCOL + h * 128 + chunk * 32), TC_INV_SLOT * 4, full, pol);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (shuffle-free form), this CTA's 128 rows =============================
+        const int quarter = warp & 3;
+        const int half = ((warp - TC_EPI_WARP0) >> 2) & 1;
+        const int sub = (warp - TC_EPI_WARP0) >> 3;
+        const uint64_t red_policy = l2_policy_evict_last();
+        const int pp = (lane >> 2) & 3;
+        const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
+        uint32_t n_tile = 0;
+        for (int it = cluster_id; it < n_items; it += n_clusters) {
+            int kc, ch, mt, seg;
+            decode(it, kc, ch, mt, seg);
+            if (!pair_active(ch, mt)) continue;
+            TcPair pr[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int row0 = quarter * 32 + 16 * hh + 4 * (lane >> 4) + pp;
+                const size_t mrow = (size_t)(ch * p.MT + mt) * TC_ROWS + row0;
+                const int t = p.row_t[mrow];
+                TcPair &r = pr[hh];
+                r.scale = p.row_scale[mrow];
+                r.ithr = p.row_ithr[mrow];
+                r.q = p.row_q[mrow];
+                r.ioff = 8 * (lane & 3) + p.row_e[mrow];
+                r.ioff_out = 8 * (lane & 3) + 2 * pp;
+                r.lo = 1;
+                r.hi = 0;
+                if (t >= 0 && r.scale != 0.f) { r.lo = p.lo[t]; r.hi = p.hi[t]; }
+                r.obase = p.cc + (size_t)(t >= 0 ? t : 0) * p.cc_pitch + r.ioff_out;
+                r.jj_full_lo = r.jj_any_lo = 1;
+                r.jj_full_hi = r.jj_any_hi = 0;
+                if (r.hi >= r.lo) {
+                    r.jj_full_lo = ceil_div8(r.lo - 2 * pp) + r.q;
+                    r.jj_full_hi = floor_div8(r.hi - 2 * pp - 1) + r.q;
+                    r.jj_any_lo = ceil_div8(r.lo - 2 * pp - 1) + r.q;
+                    r.jj_any_hi = floor_div8(r.hi - 2 * pp) + r.q;
+                }
+            }
+            const int t_begin = seg * p.seg_tiles;
+            const int t_end = (t_begin + p.seg_tiles < p.n_tiles) ? t_begin + p.seg_tiles : p.n_tiles;
+            for (int tile = t_begin; tile < t_end; tile++, n_tile++) {
+                const int s = n_tile & 1;
+                mbar_wait(acc_full + s, (n_tile >> 1) & 1);
+                tc_fence_after();
+                const int jj0 = tile * TC_NCOL + half * 128;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * TC_NCOL + half * 128);
+                int mode[2];
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const bool full = (pr[hh].hi < pr[hh].lo) || (pr[hh].jj_full_lo <= jj0 && pr[hh].jj_full_hi >= jj0 + 127);
+                    const bool any = pr[hh].jj_any_lo <= jj0 + 127 && pr[hh].jj_any_hi >= jj0;
+                    mode[hh] = !__any_sync(0xffffffffu, any) ? 0 : (__all_sync(0xffffffffu, full) ? 2 : 1);
+                }
+                if (p.debug & 1) mode[0] = mode[1] = 0;
+#pragma unroll 1
+                for (int chunk = sub; chunk < 4; chunk += TC_EPI_SUBS) {
+                    const uint32_t n_chunk = 4 * n_tile + (uint32_t)chunk;
+                    const int slot = n_chunk % TC_NI;
+                    uint64_t *full = inv_full + half * TC_NI + slot;
+                    uint32_t r0[16], r1[16];
+                    tc_ld16x128_x8(taddr + (uint32_t)(chunk * 32), r0);
+                    tc_ld16x128_x8(taddr + (16u << 16) + (uint32_t)(chunk * 32), r1);
+                    mbar_wait(full, (n_chunk / TC_NI) & 1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float *inv = inv_s + (half * TC_NI + slot) * TC_INV_SLOT;
+                    if (mode[0]) tc_epi_half2(r0, inv, pr[0], 8ll * (jj0 + chunk * 32 - pr[0].q), mode[0], red_policy);
+                    if (mode[1]) tc_epi_half2(r1, inv, pr[1], 8ll * (jj0 + chunk * 32 - pr[1].q), mode[1], red_policy);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(inv_empty + half * TC_NI + slot);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)s);  // the leader's barrier, from both CTAs
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // nobody frees tensor memory or exits while the pair still uses it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- pre-pass kernels
 // per-channel max |d| (bit pattern of a non-negative float orders like an unsigned int)
 __global__ void tc_absmax_kernel(const float *__restrict__ data, size_t N, unsigned *__restrict__ chmax) {
@@ -764,7 +1092,12 @@ struct TcGeom {
     size_t smem_bytes, dh_pitch, ci_pitch;
 };
 
-static TcGeom tc_geom(const MfShape &sh, int split) {
+static int tc_pair_mode() {  // BPMF_TC_PAIR=0 selects the one-CTA kernel (A/B measurements)
+    const char *e = getenv("BPMF_TC_PAIR");
+    return (e && atoi(e) == 0) ? 0 : 1;
+}
+
+static TcGeom tc_geom(const MfShape &sh, int split, int pair = 0) {
     TcGeom g;
     const int Kp = (int)align_up(sh.L + 14, 16);  // template length + largest row delay
     const int kc_max = split ? TC_KC_MAX_SPLIT : TC_KC_MAX;
@@ -772,7 +1105,7 @@ static TcGeom tc_geom(const MfShape &sh, int split) {
     g.Kc = (int)align_up((size_t)(Kp + g.n_kc - 1) / g.n_kc, 16);
     g.a_img_bytes = TC_ROWS * g.Kc * 2;
     g.a_bytes = g.a_img_bytes * (split ? 2 : 1);
-    g.b_slice_bytes = (8 * (TC_NCOL - 1) + g.Kc) * 2;
+    g.b_slice_bytes = (8 * ((pair ? TC_NCOL / 2 : TC_NCOL) - 1) + g.Kc) * 2;  // a CTA of a pair stages 128 of the 256 columns
     g.b_stage_bytes = (int)align_up((size_t)g.b_slice_bytes * (split ? 2 : 1), 128);
     g.smem_bytes = (size_t)g.a_bytes + TC_NB * (size_t)g.b_stage_bytes + 2 * TC_NI * TC_INV_SLOT * 4 + 320;
     const size_t n_cols = (sh.N - sh.L + TC_FRONT) / 8 + 1;  // GEMM columns that can hold a valid window start
@@ -813,6 +1146,7 @@ static TcTplWs tc_carve_templates(Workspace &ws, const MfShape &sh, const TcGeom
     TcTplWs w;
     const size_t SC = sh.SC();
     w.MT = (int)((sh.T + TC_TPL - 1) / TC_TPL);
+    w.MT += w.MT & 1;  // an even number of template tiles: the pair kernel takes them two by two
     w.aimg = ws.take<uint8_t>(SC * (size_t)w.MT * g.n_kc * g.a_bytes);
     w.row_q = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
     w.row_e = ws.take<int>(SC * (size_t)w.MT * TC_ROWS);
@@ -876,8 +1210,9 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     BPMF_REQUIRE(mf_tc_supported(sh.L, sh.step, sh.normalize, sh.network_sum),
                  "matched filter: shape not supported by the tensor path");
     BPMF_REQUIRE(!split || traces_have_lo, "matched filter: traces were prepared without the lo part");
-    const TcGeom g = tc_geom(sh, split);
     const int epi = tc_epilogue_variant();
+    const int pair = (epi == 1) ? tc_pair_mode() : 0;
+    const TcGeom g = tc_geom(sh, split, pair);
     TcTraceWs tw = tc_carve_traces(trace_ws, sh, tc_geom(sh, 0), traces_have_lo);
     TcTplWs w = tc_carve_templates(tpl_ws, sh, g);
     BPMF_REQUIRE(trace_ws.ok() && tpl_ws.ok(), "matched filter: workspace too small for the tensor path");
@@ -915,10 +1250,33 @@ int mf_tc_run(const MfShape &sh, int split, const float *d_templates, const int 
     p.debug = tc_debug_flags();
     const long long n_items = (long long)p.n_seg * p.MT * p.SC * p.n_kc;
     BPMF_REQUIRE(n_items < (1ll << 31), "matched filter: too many work items for the tensor path");
-    auto kern = epi ? mf_tc_kernel<1> : mf_tc_kernel<0>;
-    BPMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     // persistent grid: one CTA per SM, minus the SMs the caller reserved for a concurrent collective
     const int sms = std::max(1, num_sms() - reserved_sms());
+    if (pair) {
+        const long long n_pair_items = (long long)p.n_seg * (p.MT / 2) * p.SC * p.n_kc;
+        BPMF_CUDA(cudaFuncSetAttribute(mf_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+        const int n_clusters = (int)std::min<long long>(n_pair_items, (long long)std::max(1, sms / 2));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * n_clusters));
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = g.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        {
+            MainKernelTimer timer(st);
+            BPMF_CUDA(cudaLaunchKernelEx(&cfg, mf_tc_pair_kernel, p));
+        }
+        BPMF_LAUNCH_CHECK();
+        return BPMF_OK;
+    }
+    auto kern = epi ? mf_tc_kernel<1> : mf_tc_kernel<0>;
+    BPMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     const int grid = (int)std::min<long long>(n_items, (long long)sms);
     {
         MainKernelTimer timer(st);

@@ -90,6 +90,28 @@ def matched_filter(templates, moveouts, weights, data, step, arch="gpu", check_z
     return out
 
 
+class hold_traces:
+    """``with hold_traces(data) as data: ...`` -- every ``matched_filter`` call made on ``data`` inside the block
+    reuses ONE upload + staging of the traces (BPMF loops template chunks over one day of data, one call per chunk,
+    BPMF/similarity_search.py:773-790; without the hold each call moves the 1.7-3.3 GB day again).  The block
+    promises that ``data`` is not modified meanwhile.  ``data`` must be C-contiguous float32 -- the array returned
+    by ``__enter__`` is (a copy is made otherwise) and is the one to pass to ``matched_filter``."""
+
+    def __init__(self, data):
+        self.data = _as(data, np.float32)
+
+    def __enter__(self):
+        lib = _lib.load()
+        _lib.require_device()
+        S, Cc, N = self.data.shape
+        _lib.check(lib.bpmf_mf_hold_traces(_ptr(self.data, C.c_float), N, S, Cc), "hold_traces")
+        return self.data
+
+    def __exit__(self, *exc):
+        _lib.load().bpmf_mf_release_traces()
+        return False
+
+
 def _report_zeros(cc_sums, moveouts, weights, step, mode):
     """Upstream prints how many CCs are exactly zero per template (8_template_matching.ipynb:373)."""
     n_templates = cc_sums.shape[0] if mode == "all" else min(1, cc_sums.shape[0])

@@ -9,16 +9,17 @@ positions in between ("outputs hashed + max-abs-diff vs oracle on 
 """
 import numpy as np
 
-SEGMENT = 65536  # samples swept per resident template image (TC_SEG_TILES * 2048 in csrc/mf_tc.cu)
+SEGMENT = 131072  # samples swept per resident template image (TC_SEG_TILES * 2048 in csrc/mf_tc.cu)
 
 
 def window_starts(n_corr, n_windows, win_len, gap=None, planted=(), mv_range=(-100, 3000), L=800, seed=7):
     """Start indices of `n_windows` runs of `win_len` outputs in [0, n_corr)."""
     rng = np.random.default_rng(seed)
     must = [0, n_corr - win_len]
-    n_seg = max(1, n_corr // SEGMENT)
-    for k in sorted({1, n_seg // 2, n_seg - 1, n_seg}):  # both sides of a few segment boundaries
-        must.append(k * SEGMENT - win_len // 2)
+    for seg in (SEGMENT, SEGMENT // 2):  # both sides of a few segment boundaries (64- and 32-tile segments)
+        n_seg = max(1, n_corr // seg)
+        for k in sorted({1, n_seg // 2, n_seg - 1, n_seg}):
+            must.append(k * seg - win_len // 2)
     if gap is not None:  # outputs whose windows enter / leave the zero gap, for every moveout in range
         g0, g1 = gap
         must += [g0 - mv_range[1] - L - win_len // 2, g0 - mv_range[1] // 2 - L, g0 - win_len // 2, (g0 + g1) // 2,

@@ -114,3 +114,28 @@ def test_grid_thinning_pattern():
     red = clib.find_similar_sources(tts, lon, lat, cell_lon, cell_lat, 0.1, num_threads=4, num_stations_for_diff=5)
     want = libc_numpy.find_similar_moveouts(tts, lon, lat, cell_lon, cell_lat, 0.1, 5, 2).astype(bool)
     assert red.dtype == bool and np.array_equal(red, want) and 0 < red.sum() < K
+
+
+def test_template_chunk_loop_reuses_held_traces():
+    """run_matched_filter_search's chunk loop (BPMF/similarity_search.py:773-790): several calls on the same day of
+    traces.  Inside hold_traces the day is uploaded and staged once; results are identical to the plain calls, a
+    change of the array after the block is seen again, and the launch counter shows the staging kernels were skipped."""
+    from seismic_bpmf_b200 import _lib
+
+    lib = _lib.load()
+    tp, mv, w, d, _ = _synth.mf_case(48, 4, 3, 400, 60000, seed=21)
+    plain = [fmf.matched_filter(tp[a:a + 16], mv[a:a + 16], w[a:a + 16], d, 1, check_zeros=False) for a in (0, 16, 32)]
+    n0 = lib.bpmf_launch_count()
+    fmf.matched_filter(tp[:16], mv[:16], w[:16], d, 1, check_zeros=False)
+    per_call = lib.bpmf_launch_count() - n0
+    with fmf.hold_traces(d) as dd:
+        n0 = lib.bpmf_launch_count()
+        held = [fmf.matched_filter(tp[a:a + 16], mv[a:a + 16], w[a:a + 16], dd, 1, check_zeros=False) for a in (0, 16, 32)]
+        n_held = lib.bpmf_launch_count() - n0
+    for a, b in zip(plain, held):  # same arithmetic; the order of the fp32 reductions differs from run to run
+        assert np.abs(a - b).max() < 1e-6 and np.array_equal(a == 0, b == 0)
+    assert n_held < 3 * per_call  # the trace-side kernels ran once, not three times
+    d2 = d.copy()
+    d2[0, 0, 1000:2000] *= 3.0
+    after = fmf.matched_filter(tp[:16], mv[:16], w[:16], d2, 1, check_zeros=False)
+    assert np.abs(after - cpu.matched_filter(tp[:16], mv[:16], w[:16], d2, 1)).max() < 1e-4

@@ -78,8 +78,9 @@ def test_cfg2_full_day_every_tile_vs_oracle(weighting):
     structural, chance = _parity.zero_pattern(got, want)
     assert structural == 0 and chance <= 4, (structural, chance)
     m = mv[torch.from_numpy(whole).cuda()].cpu().numpy()
+    used = w[torch.from_numpy(whole).cuda()].cpu().numpy() != 0  # the range is set by the WEIGHTED channels only
     for r in range(2):
-        lo_r, hi_r = max(0, -int(m[r].min())), N - L - int(m[r].max())
+        lo_r, hi_r = max(0, -int(m[r][used[r]].min())), N - L - int(m[r][used[r]].max())
         assert not got[r, :lo_r].any() and not got[r, hi_r + 1:].any()
         assert not want[r, :lo_r].any() and not want[r, hi_r + 1:].any()
     # (3) planted detections are the global maxima, at indices on both sides of 2^23
