@@ -284,6 +284,18 @@ int bpmf_detect_dev(const float *d_series, size_t pitch, size_t n_series, const 
                     size_t search_win, int mode, void *d_workspace, size_t workspace_bytes,
                     unsigned *d_count, int *d_series_idx, int *d_index, float *d_value, float *d_thr_value,
                     size_t capacity, void *stream);
+/* The same with the two remaining per-template steps of MatchedFilter.find_detections folded in:
+ *   d_thr_cap (n_series floats or NULL): threshold = min(cap, threshold), the caller passing
+ *     max_CC_threshold * sum(weights) per template (BPMF/similarity_search.py:629);
+ *   use_kurtosis / max_kurtosis: a row whose excess kurtosis (scipy.stats.kurtosis defaults, all
+ *     num_samples samples, float64) exceeds max_kurtosis detects nothing -- the reference zeroes such a
+ *     CC series (similarity_search.py:633-642); d_kurtosis_out (n_series floats or NULL) receives the values. */
+int bpmf_detect_gated_dev(const float *d_series, size_t pitch, size_t n_series, const float *d_gaussian_sample,
+                          float num_dev, size_t num_samples, size_t half_window_samp, size_t shift_samp,
+                          size_t search_win, int mode, const float *d_thr_cap, int use_kurtosis,
+                          float max_kurtosis, float *d_kurtosis_out, void *d_workspace, size_t workspace_bytes,
+                          unsigned *d_count, int *d_series_idx, int *d_index, float *d_value,
+                          float *d_thr_value, size_t capacity, void *stream);
 
 /* ---------------------------------------------------------------- (2d) backprojection peak picking
  * The index part of Beamformer.find_detections (BPMF/template_search.py:603-610): utils._detect_peaks(maxbeam,

@@ -86,6 +86,8 @@ _SIGNATURES = {
     "_compute_std": (C.c_float, [fp, C.c_float, z]),
     "bpmf_threshold_workspace_bytes": (z, [z, z, z, z]),
     "bpmf_detect_dev": (C.c_int, [vp, z, z, vp, C.c_float, z, z, z, z, C.c_int, vp, z, vp, vp, vp, vp, vp, z, vp]),
+    "bpmf_detect_gated_dev": (C.c_int, [vp, z, z, vp, C.c_float, z, z, z, z, C.c_int, vp, C.c_int, C.c_float, vp, vp, z,
+                                        vp, vp, vp, vp, vp, z, vp]),
     "bpmf_time_dependent_threshold_dev": (C.c_int, [vp, z, z, vp, C.c_float, z, z, z, vp, z, vp, z, vp]),
 }
 

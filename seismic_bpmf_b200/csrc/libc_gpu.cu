@@ -159,6 +159,44 @@ __global__ void thr_expand_kernel(const float *__restrict__ tw, size_t n_win, si
     thr[b * thr_pitch + i] = thr_at(tw + b * n_win, n_win, n, shift, i);
 }
 
+// Excess kurtosis of each whole series, scipy.stats.kurtosis defaults (population moments, Fisher): the sanity check
+// of MatchedFilter.find_detections (BPMF/similarity_search.py:633-642) zeroes a CC series whose kurtosis exceeds
+// max_kurto.  Two passes in double precision: mean, then the 2nd and 4th central moments.
+struct SeriesMoments {
+    double sum, m2, m4;
+    float kurtosis, pad;
+};
+template <int PASS>
+__global__ void series_moments_kernel(const float *__restrict__ x, size_t pitch, size_t n,
+                                      SeriesMoments *__restrict__ mo) {
+    const size_t b = blockIdx.y;
+    const float *xs = x + b * pitch;
+    const double mean = (PASS == 1) ? mo[b].sum / (double)n : 0.0;
+    double a2 = 0.0, a4 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (PASS == 0) a2 += (double)xs[i];
+        else {
+            const double d = (double)xs[i] - mean, d2 = d * d;
+            a2 += d2;
+            a4 += d2 * d2;
+        }
+    }
+    a2 = warp_sum(a2);
+    if (PASS == 1) a4 = warp_sum(a4);
+    if ((threadIdx.x & 31) == 0) {
+        if (PASS == 0) atomicAdd(&mo[b].sum, a2);
+        else { atomicAdd(&mo[b].m2, a2); atomicAdd(&mo[b].m4, a4); }
+    }
+}
+__global__ void series_kurtosis_finish_kernel(SeriesMoments *mo, size_t B, size_t n, float *__restrict__ out) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double m2 = mo[b].m2 / (double)n, m4 = mo[b].m4 / (double)n;
+    const float k = (m2 > 0.0) ? (float)(m4 / (m2 * m2) - 3.0) : nanf("");  // scipy returns nan for a constant series
+    mo[b].kurtosis = k;
+    if (out) out[b] = k;
+}
+
 // Candidate detections straight from the CC slab: sample i of series b is reported when
 // cc > threshold(i) and, in mode 1, it also survives the declustering of select_cc_indexes
 // (libc.c:441-485, closed form below).  Survivors are appended to a compact list; only that list has to
@@ -166,13 +204,17 @@ __global__ void thr_expand_kernel(const float *__restrict__ tw, size_t n_win, si
 __global__ void detect_kernel(const float *__restrict__ x, size_t pitch, const float *__restrict__ tw, size_t n_win,
                               size_t n, size_t shift, long long search_win, int mode, unsigned *__restrict__ count,
                               int *__restrict__ o_series, int *__restrict__ o_index, float *__restrict__ o_value,
-                              float *__restrict__ o_thr, unsigned capacity) {
+                              float *__restrict__ o_thr, unsigned capacity, const float *__restrict__ thr_cap,
+                              const SeriesMoments *__restrict__ mo, float max_kurtosis) {
     const size_t b = blockIdx.y;
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (long long)n) return;
+    // similarity_search.py:637-642: a series whose kurtosis exceeds max_kurto is zeroed -> it detects nothing
+    if (mo != nullptr && mo[b].kurtosis > max_kurtosis) return;
     const float *cc = x + b * pitch;
     const float v = cc[j];
-    const float th = thr_at(tw + b * n_win, n_win, n, shift, (size_t)j);
+    float th = thr_at(tw + b * n_win, n_win, n, shift, (size_t)j);
+    if (thr_cap != nullptr) th = fminf(thr_cap[b], th);  // similarity_search.py:629: np.minimum(max_CC_threshold * sum(w), thr)
     bool keep = v > th;
     if (keep && mode == 1) {
         const long long a = (j <= search_win) ? 0 : j - search_win;
@@ -212,6 +254,7 @@ extern "C" size_t bpmf_threshold_workspace_bytes(size_t n_series, size_t n, size
     Workspace ws(nullptr, 0);
     ws.take<ThrStat>(n_series);
     ws.take<float>(n_series * n_win);
+    ws.take<SeriesMoments>(n_series);
     return ws.used;
 }
 
@@ -265,10 +308,12 @@ extern "C" int bpmf_time_dependent_threshold_dev(float *d_series, size_t pitch, 
     return BPMF_OK;
 }
 
-extern "C" int bpmf_detect_dev(const float *d_series, size_t pitch, size_t B, const float *d_gauss, float num_dev,
-                               size_t n, size_t half, size_t shift, size_t search_win, int mode, void *d_workspace,
-                               size_t workspace_bytes, unsigned *d_count, int *d_series_idx, int *d_index,
-                               float *d_value, float *d_thr_value, size_t capacity, void *stream) {
+extern "C" int bpmf_detect_gated_dev(const float *d_series, size_t pitch, size_t B, const float *d_gauss,
+                                     float num_dev, size_t n, size_t half, size_t shift, size_t search_win, int mode,
+                                     const float *d_thr_cap, int use_kurtosis, float max_kurtosis,
+                                     float *d_kurtosis_out, void *d_workspace, size_t workspace_bytes,
+                                     unsigned *d_count, int *d_series_idx, int *d_index, float *d_value,
+                                     float *d_thr_value, size_t capacity, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     BPMF_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned), st));
     if (B == 0) return BPMF_OK;
@@ -280,16 +325,36 @@ extern "C" int bpmf_detect_dev(const float *d_series, size_t pitch, size_t B, co
     Workspace ws(d_workspace, workspace_bytes);
     ThrStat *stat = ws.take<ThrStat>(B);
     float *tw = ws.take<float>(B * n_win);
+    SeriesMoments *mo = ws.take<SeriesMoments>(B);
     BPMF_REQUIRE(ws.ok(), "detect: workspace too small");
+    if (use_kurtosis) {
+        BPMF_CUDA(cudaMemsetAsync(mo, 0, sizeof(SeriesMoments) * B, st));
+        const dim3 grid(64, (unsigned)B);
+        series_moments_kernel<0><<<grid, 256, 0, st>>>(d_series, pitch, n, mo);
+        BPMF_LAUNCH_CHECK();
+        series_moments_kernel<1><<<grid, 256, 0, st>>>(d_series, pitch, n, mo);
+        BPMF_LAUNCH_CHECK();
+        series_kurtosis_finish_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(mo, B, n, d_kurtosis_out);
+        BPMF_LAUNCH_CHECK();
+    }
     // the series is NOT modified: zeros are substituted on the fly inside the window statistics
     int rc = thr_windows(const_cast<float *>(d_series), pitch, B, d_gauss, num_dev, n, W, shift, n_win, false, stat,
                          tw, st);
     if (rc != BPMF_OK) return rc;
     detect_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)B), 256, 0, st>>>(
         d_series, pitch, tw, n_win, n, shift, (long long)search_win, mode, d_count, d_series_idx, d_index, d_value,
-        d_thr_value, (unsigned)capacity);
+        d_thr_value, (unsigned)capacity, d_thr_cap, use_kurtosis ? mo : nullptr, max_kurtosis);
     BPMF_LAUNCH_CHECK();
     return BPMF_OK;
+}
+
+extern "C" int bpmf_detect_dev(const float *d_series, size_t pitch, size_t B, const float *d_gauss, float num_dev,
+                               size_t n, size_t half, size_t shift, size_t search_win, int mode, void *d_workspace,
+                               size_t workspace_bytes, unsigned *d_count, int *d_series_idx, int *d_index,
+                               float *d_value, float *d_thr_value, size_t capacity, void *stream) {
+    return bpmf_detect_gated_dev(d_series, pitch, B, d_gauss, num_dev, n, half, shift, search_win, mode, nullptr, 0,
+                                 0.f, nullptr, d_workspace, workspace_bytes, d_count, d_series_idx, d_index, d_value,
+                                 d_thr_value, capacity, stream);
 }
 
 static int thr_host(float *x, float *gauss, float num_dev, size_t n, size_t half, size_t shift, float *thr) {

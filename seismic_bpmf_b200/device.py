@@ -254,17 +254,26 @@ class DetectBatches:
         self.value = torch.empty((self.n_batches, self.capacity), dtype=torch.float32, device=self.device)
         self.thr = torch.empty((self.n_batches, self.capacity), dtype=torch.float32, device=self.device)
 
-    def run(self, k, series, gaussian_sample, num_dev, search_win=0, mode="select"):
-        """Enqueue the detection of batch ``k`` on ``series`` (B' <= B rows of a (.., pitch) device slab)."""
+    def run(self, k, series, gaussian_sample, num_dev, search_win=0, mode="select", thr_cap=None, max_kurtosis=None,
+            kurtosis_out=None):
+        """Enqueue the detection of batch ``k`` on ``series`` (B' <= B rows of a (.., pitch) device slab).
+        ``thr_cap`` (B' floats on the device): threshold = min(cap, threshold) -- ``max_CC_threshold * sum(weights)``
+        of similarity_search.py:629; ``max_kurtosis``: rows whose excess kurtosis exceeds it detect nothing
+        (similarity_search.py:633-642); ``kurtosis_out`` (B' floats) receives the kurtosis values."""
         assert series.is_cuda and series.dtype == torch.float32 and series.dim() == 2 and series.stride(1) == 1
         assert series.shape[0] <= self.B and 0 <= k < self.n_batches
         g = _chk(gaussian_sample, torch.float32, "gaussian_sample")
-        rc = self.lib.bpmf_detect_dev(series.data_ptr(), series.stride(0), series.shape[0], g.data_ptr(), float(num_dev),
-                                      self.n, self.half, self.shift, int(search_win), 1 if mode == "select" else 0,
-                                      self.workspace.data_ptr(), self.workspace.numel(), self.count[k:].data_ptr(),
-                                      self.series[k].data_ptr(), self.index[k].data_ptr(), self.value[k].data_ptr(),
-                                      self.thr[k].data_ptr(), self.capacity, _stream_ptr())
-        _lib.check(rc, "detect_dev")
+        if thr_cap is not None:
+            thr_cap = _chk(thr_cap, torch.float32, "thr_cap")
+            assert thr_cap.numel() == series.shape[0]
+        rc = self.lib.bpmf_detect_gated_dev(
+            series.data_ptr(), series.stride(0), series.shape[0], g.data_ptr(), float(num_dev), self.n, self.half,
+            self.shift, int(search_win), 1 if mode == "select" else 0, thr_cap.data_ptr() if thr_cap is not None else None,
+            0 if max_kurtosis is None else 1, 0.0 if max_kurtosis is None else float(max_kurtosis),
+            kurtosis_out.data_ptr() if kurtosis_out is not None else None, self.workspace.data_ptr(),
+            self.workspace.numel(), self.count[k:].data_ptr(), self.series[k].data_ptr(), self.index[k].data_ptr(),
+            self.value[k].data_ptr(), self.thr[k].data_ptr(), self.capacity, _stream_ptr())
+        _lib.check(rc, "detect_gated_dev")
 
     def packed(self):
         """Device tensors (count (n_batches,), series, index, value, thr (n_batches, capacity)); no sync."""

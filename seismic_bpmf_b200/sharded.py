@@ -164,11 +164,13 @@ def gather_detections(series, index, value, thr, group=None, device=None):
 
 def matched_filter_detect_sharded(templates, moveouts, weights, data, gaussian_sample, num_dev, window_samp,
                                   overlap=0.25, search_win=0, step=1, normalize="short", precision="auto", group=None,
-                                  batch=64, capacity=1 << 18, compute=None, detect=None):
+                                  batch=64, capacity=1 << 18, compute=None, detect=None, max_cc_threshold=None,
+                                  max_kurtosis=None):
     """The multi-GPU detection path: every rank runs the matched filter on its block of templates, thresholds and
     declusters ITS OWN CC rows on the device (rms threshold of BPMF/libc.c:516-673 with ``half_window =
     window_samp // 2``, ``shift = int((1 - overlap) * window_samp)`` as BPMF/clib.py:296-297, then
-    ``select_cc_indexes`` with ``search_win``), and only the detections are all-gathered.  The CC slab never
+    ``select_cc_indexes`` with ``search_win``; optionally the threshold cap ``max_cc_threshold * sum(weights)`` and
+    the kurtosis sanity check of similarity_search.py:629-642), and only the detections are all-gathered.  The CC slab never
     leaves the GPU that made it and is never held for more than ``batch`` templates at a time, so
     BASELINE.json configs[3] (172.8 GB of CC) needs no more memory than one batch.
 
@@ -205,7 +207,11 @@ def matched_filter_detect_sharded(templates, moveouts, weights, data, gaussian_s
         for k, t0 in enumerate(range(0, n_local, batch)):
             n_here = min(batch, n_local - t0)
             plan.run_batch(tp, mv, w, data, t0, n_here, cc_row0=0)
-            det.run(k, plan.cc[:n_here], gaussian_sample, num_dev, search_win=search_win, mode="select")
+            cap = None
+            if max_cc_threshold is not None:
+                cap = (float(max_cc_threshold) * w[t0: t0 + n_here].sum(dim=(1, 2))).float().contiguous()
+            det.run(k, plan.cc[:n_here], gaussian_sample, num_dev, search_win=search_win, mode="select", thr_cap=cap,
+                    max_kurtosis=max_kurtosis)
         s_, i_, v_, t_ = det.collect(series_offsets=[lo + k * batch for k in range(n_batches)])
     else:
         s_, i_, v_, t_ = (np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32),

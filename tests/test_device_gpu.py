@@ -122,3 +122,41 @@ def test_host_path_reuses_cached_buffers():
     lib.bpmf_release_cache()
     got = fmf.matched_filter(tp[:3], mv[:3], w[:3], d, 1, precision="fp32", check_zeros=False)
     assert np.abs(got - want[:3]).max() < 2e-6
+
+
+def test_detect_gated_threshold_cap_and_kurtosis_gate():
+    """The two remaining per-template steps of MatchedFilter.find_detections on the device: the threshold cap
+    max_CC_threshold * sum(w) (similarity_search.py:629) and the kurtosis sanity check (:633-642)."""
+    import torch
+    from scipy.stats import kurtosis as sk
+
+    from oracle import libc_numpy
+    from seismic_bpmf_b200 import device as dev
+
+    rng = np.random.default_rng(9)
+    n, win = 60000, 6000
+    x = (0.03 * rng.standard_normal((3, n))).astype(np.float32)
+    x[0, 20000] = 0.5            # a clean detection
+    x[1, 30000] = 0.5
+    x[1, 5000:9000] *= 12.0      # a burst: kurtosis far above 20 -> the whole series is discarded
+    x[2, 40000] = 0.2            # below the rms threshold of this noisy series, above the cap
+    x[2, 10000:30000] *= 3.0
+    wn = rng.standard_normal(500).astype(np.float32)
+    d = torch.device("cuda")
+    xs, g = torch.from_numpy(x).to(d), torch.from_numpy(wn).to(d)
+    det = dev.DetectBatches(1, 3, n, win // 2, int(0.75 * win), capacity=4096, device=d)
+    kout = torch.zeros(3, device=d)
+    cap = torch.tensor([1.0, 1.0, 0.15], device=d)
+    det.run(0, xs, g, 8.0, search_win=500, mode="select", thr_cap=cap, max_kurtosis=20.0, kurtosis_out=kout)
+    s_, i_, v_, t_ = det.collect()
+    want_k = sk(x.astype(np.float64), axis=1)
+    assert np.abs(kout.cpu().numpy() - want_k).max() < 1e-3 * np.abs(want_k).max()
+    assert want_k[1] > 20.0 > want_k[0]
+    got = set(zip(s_.tolist(), i_.tolist()))
+    assert (0, 20000) in got and (2, 40000) in got
+    assert not any(s == 1 for s, _ in got)                     # gated out by its kurtosis
+    for b in (0, 2):                                            # everything else follows the capped threshold
+        thr, _ = libc_numpy.time_dependent_threshold(x[b], wn, 8.0, win // 2, int(0.75 * win))
+        thr = np.minimum(float(cap[b]), thr)
+        sel = np.flatnonzero(libc_numpy.select_cc_indexes(x[b], thr.astype(np.float32), 500))
+        assert sorted(i for s, i in got if s == b) == sel.tolist()
