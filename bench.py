@@ -616,7 +616,7 @@ def run_ours(args, rank, world, local_rank):
             mult = 3.0 if prec_name == "fp16x3" else 1.0
             roof = {"bound": "tensor", "achieved": tflops * mult, "peak": pk["tensor_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": tflops * mult / pk["tensor_tflops_sustained"],
-                    "traffic": measured_traffic("mf_tc_kernel", T, S, Cc, L, N),
+                    "traffic": None if os.environ.get("BPMF_TC_PAIR", "0") == "1" else measured_traffic("mf_tc_kernel", T, S, Cc, L, N),
                     "peak_source": pk["source"] + " (sustained bf16 cuBLAS; fp16 runs at the same tensor rate)",
                     "algorithmic_tflops": tflops, "kernel_ms": kernel_ms, "kernel": "mf_tc_kernel",
                     "kernel_ms_is": "sum of the main-kernel launches of one step on rank 0 (%d per step)" % len(schedule),
@@ -641,8 +641,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs (%.2f GB) and output (%.2f GB) exceed the 126 MB L2" % (
                        (S * Cc * N * 4 + T * S * Cc * L * 4) / 1e9, T * n_corr * 4 / 1e9),
                    "collective": collective,
-                   "epilogue": "shuffle-free (16x128b TMEM loads, red.v2)" if os.environ.get("BPMF_TC_EPI", "1") != "0"
-                   else "r1 (32x32b TMEM loads, butterfly transpose, red.v4)"},
+                   "kernel": ("CTA pairs (tcgen05 cta_group::2)" if os.environ.get("BPMF_TC_PAIR", "0") == "1" else "one CTA per SM")
+                   + (", shuffle-free epilogue (16x128b TMEM loads, red.v2)" if os.environ.get("BPMF_TC_EPI", "1") != "0"
+                      else ", r1 epilogue (32x32b TMEM loads, butterfly transpose, red.v4)")},
         "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks,
         "parity": parity, "variants": variants, "e2e_fused_detection": fused, "cfg4": cfg4, "beamform": beam, "libc": libc,
     }

@@ -41,7 +41,7 @@ constexpr int TC_TPL = 16;          // templates per tile
 constexpr int TC_NCOL = 256;        // GEMM columns per tile (= 2048 samples)
 constexpr int TC_KC_MAX = 816;      // resident A, single pass: 128 x 816 fp16 = 208 896 B
 constexpr int TC_KC_MAX_SPLIT = 384; // resident A, hi + lo images: 128 x 384 x 2 x 2 = 196 608 B
-constexpr int TC_SEG_TILES = 64;    // tiles swept per resident A image (131 072 samples)
+constexpr int TC_SEG_TILES = 32;    // tiles swept per resident A image (65 536 samples)
 #ifndef TC_EPI_WARPS
 #define TC_EPI_WARPS 16             // 8 or 16: with 16, two warps share each (lane quarter, tile half) and take alternate chunks
 #endif
@@ -1092,9 +1092,14 @@ struct TcGeom {
     size_t smem_bytes, dh_pitch, ci_pitch;
 };
 
-static int tc_pair_mode() {  // BPMF_TC_PAIR=0 selects the one-CTA kernel (A/B measurements)
+// BPMF_TC_PAIR=1 selects the CTA-pair kernel (tcgen05 cta_group::2).  Measured on this pool (profiles/
+// r2_matched_filter_tc.md): it needs 25-30 % fewer SM cycles per pass, but under the 1 kW power cap the clock settles
+// that much lower (1.05-1.10 GHz against 1.40-1.45 GHz) and the pass takes the same 310-320 ms, with about twice the
+// DRAM traffic -- so the one-CTA kernel stays the default and the pair kernel is kept for parts that are not
+// power-capped at this point.
+static int tc_pair_mode() {
     const char *e = getenv("BPMF_TC_PAIR");
-    return (e && atoi(e) == 0) ? 0 : 1;
+    return (e && atoi(e) == 1) ? 1 : 0;
 }
 
 static TcGeom tc_geom(const MfShape &sh, int split, int pair = 0) {

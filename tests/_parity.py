@@ -9,7 +9,7 @@ positions in between ("outputs hashed + max-abs-diff vs oracle on 
 """
 import numpy as np
 
-SEGMENT = 131072  # samples swept per resident template image (TC_SEG_TILES * 2048 in csrc/mf_tc.cu)
+SEGMENT = 65536  # samples swept per resident template image (TC_SEG_TILES * 2048 in csrc/mf_tc.cu)
 
 
 def window_starts(n_corr, n_windows, win_len, gap=None, planted=(), mv_range=(-100, 3000), L=800, seed=7):
