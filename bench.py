@@ -542,6 +542,25 @@ def run_ours(args, rank, world, local_rank):
             e2e["note"] = ("every rank's process downloads its own (T/N, n_corr) block into pinned host memory: the figure "
                            "is bounded by the host's aggregate ingest (aggregate_d2h_gbs), see e2e_fused_detection for the "
                            "path that returns detections instead of the CC slab")
+        # BPMF's template-chunk loop (similarity_search.py:773-790): three successive calls on the SAME day of traces,
+        # without and with fast_matched_filter.hold_traces (one upload + staging of the day instead of one per chunk)
+        if world == 1:
+            def chunk_loop():
+                def three_calls(dd):
+                    t0_ = time.perf_counter()
+                    for _ in range(3):
+                        fmf.matched_filter(h["tp"], h["mv"], h["w"], dd, step, arch="gpu", precision=args.precision,
+                                           check_zeros=False, out=out_np)
+                    return (time.perf_counter() - t0_) / 3
+                plain = three_calls(h["data"])
+                with fmf.hold_traces(h["data"]) as dd:
+                    three_calls(dd)  # first call inside the block stages the traces
+                    held = three_calls(dd)
+                return {"ms_per_chunk_plain": 1e3 * plain, "ms_per_chunk_held": 1e3 * held,
+                        "what": "3 chunks of %d templates on one day of traces through fast_matched_filter.matched_filter; held = "
+                                "inside fast_matched_filter.hold_traces (no re-upload / re-staging of the %.2f GB day)"
+                                % (T, h["data"].nbytes / 1e9)}
+            e2e["template_chunk_loop"] = guarded(chunk_loop)
         bpmf_release = getattr(lib, "bpmf_release_cache", None)
         if bpmf_release:
             bpmf_release()
