@@ -384,6 +384,7 @@ static std::mutex g_cache_mu;
 
 static cudaError_t cache_get(HostCache &c, int slot, size_t bytes, void **out) {
     if (c.cap[slot] < bytes) {
+        if (slot <= 1) c.staged = false;  // the traces (slot 0) or their staging (slot 1) move
         if (c.ptr[slot]) cudaFree(c.ptr[slot]);
         c.ptr[slot] = nullptr;
         c.cap[slot] = 0;
@@ -400,6 +401,7 @@ static void cache_release(HostCache &c) {
         c.ptr[i] = nullptr;
         c.cap[i] = 0;
     }
+    c.staged = false;  // a held day has to be uploaded and staged again
 }
 }  // namespace bpmf
 
