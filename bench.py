@@ -330,7 +330,7 @@ def run_ours(args, rank, world, local_rank):
         planted = {}
     # N > 1: the per-rank pass runs in template batches so that the all-gather of one batch's CC slab
     # overlaps the kernels of the next one
-    batch = T if world == 1 else (args.batch or (128 if world <= 2 else 64))
+    batch = T if world == 1 else (args.batch or (128 if world <= 2 else (64 if world <= 4 else 32)))
     plan = dev.MatchedFilterPlan(T, S, Cc, L, N, step=step, precision=args.precision, device=device, batch=batch)
     n_corr = plan.n_corr
     units = T * S * Cc * n_corr  # per rank, per step

@@ -83,17 +83,20 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES]
     out = lib_path()
     if force or jobs or _stale(out, objs):
-        cmd = [nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        # link to a temporary name and rename: a snapshot of the tree never sees a half-written library
+        cmd = [nvcc, "-shared", "-o", out + ".tmp"] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+        os.replace(out + ".tmp", out)
     fobjs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in FEATURES_SOURCES]
     fout = features_lib_path()
     if force or jobs or _stale(fout, fobjs):
-        cmd = [nvcc, "-shared", "-o", fout] + fobjs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcufft"]
+        cmd = [nvcc, "-shared", "-o", fout + ".tmp"] + fobjs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcufft"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+        os.replace(fout + ".tmp", fout)
     link = os.path.join(LIBDIR, "libc.so")
     if not os.path.islink(link) and not os.path.exists(link):
         os.symlink(LIBNAME, link)

@@ -316,8 +316,13 @@ class PeerSlabGather:
     device-side barrier per batch tells every rank that the batch is complete everywhere.
     """
 
-    def __init__(self, n_elements_per_rank, device, group=None, n_buffers=2, n_streams=3):
+    def __init__(self, n_elements_per_rank, device, group=None, n_buffers=2, n_streams=None):
+        import os
+
         import torch.distributed._symmetric_memory as symm_mem
+
+        if n_streams is None:  # one copy stream per peer keeps more copy engines / NVLink ports busy at once
+            n_streams = int(os.environ.get("BPMF_GATHER_STREAMS", "0")) or 7
 
         group = dist.group.WORLD if group is None else group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
