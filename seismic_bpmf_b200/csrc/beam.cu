@@ -401,11 +401,7 @@ __global__ void __launch_bounds__(128)
 // Groups of one or two sources (unrelated moveouts) are not worth a staged window: beam_pack_kernel lists
 // their sources and beam_direct_kernel gathers them straight from the L2-resident rows (4 B per gather-FMA
 // either way, without the per-row hand-shake); both kernels merge into the same (max, argmax) keys.
-// r2: when every weighted member of the group carries the SAME weight on the row (uniform or 0/c source weights --
-// what BPMF builds, template_search.py:770-798), the record holds a table of offsets only (4 instead of 8 broadcast
-// LDS.128 per consumer warp) and the weight + the mask of weighted positions travel in the header; the arithmetic is
-// the same fmaf(weight, sample, acc) per position, so the bits do not change.
-constexpr int F_ROW_DENSE = 0, F_ROW_SPARSE = 2, F_END = 1, F_ROW_UNI_DENSE = 4, F_ROW_UNI_SPARSE = 6;
+constexpr int F_ROW_DENSE = 0, F_ROW_SPARSE = 2, F_END = 1;
 
 template <bool REDUCE_MAX, int SPLIT>
 __global__ void __launch_bounds__(F_THREADS, 2)
@@ -502,23 +498,11 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                     int *hdr = reinterpret_cast<int *>(st + F_WIN + 2 * F_G);
                     const long long wlo = align4_down((long long)mn);
                     const int dense = __popc(nz) > F_G / 2;
-                    const float wu = __shfl_sync(0xffffffffu, b, __ffs(nz) - 1);  // weight of the first weighted member
-                    const bool uniform = __all_sync(0xffffffffu, b == 0.f || b == wu);
-                    if (uniform) {
-                        if (lane < F_G)
-                            reinterpret_cast<int *>(st + F_WIN)[lane] = (b != 0.f) ? (int)((long long)tv - wlo) : (int)(zero_s - st);
-                        if (lane == 0) {
-                            hdr[0] = dense ? F_ROW_UNI_DENSE : F_ROW_UNI_SPARSE;
-                            hdr[1] = __float_as_int(wu);
-                            hdr[2] = (int)(nz & 0xffffu);
-                        }
-                    } else {
-                        if (lane < F_G)
-                            reinterpret_cast<int2 *>(st + F_WIN)[lane] =
-                                (b != 0.f) ? make_int2((int)((long long)tv - wlo), __float_as_int(b))
-                                           : make_int2((int)(zero_s - st), 0);
-                        if (lane == 0) hdr[0] = dense ? F_ROW_DENSE : F_ROW_SPARSE;
-                    }
+                    if (lane < F_G)
+                        reinterpret_cast<int2 *>(st + F_WIN)[lane] =
+                            (b != 0.f) ? make_int2((int)((long long)tv - wlo), __float_as_int(b))
+                                       : make_int2((int)(zero_s - st), 0);
+                    if (lane == 0) hdr[0] = dense ? F_ROW_DENSE : F_ROW_SPARSE;
                     // samples [g0, g0 + len) of the row are needed; the part outside [0, pitch) reads as zero
                     const long long g0 = t0 + wlo;                                      // multiple of 4
                     const int len = (int)(((long long)mx - wlo + F_TT + 3) & ~3ll);     // <= F_WIN
@@ -579,39 +563,10 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                     mbar_wait(full + stage, (it / F_NSTAGE) & 1);
                     it++;
                     const float *st = stages + stage * F_STAGE;
-                    const int4 hd = *reinterpret_cast<const int4 *>(st + F_WIN + 2 * F_G);  // kind, weight, mask
-                    const int kind = hd.x;
+                    const int kind = reinterpret_cast<const int *>(st + F_WIN + 2 * F_G)[0];
                     // (offset, weight) of this warp's positions 2q, 2q + 1
                     const int4 *pk4 = reinterpret_cast<const int4 *>(st + F_WIN) + half * (F_GW / 2);
-                    if (kind == F_ROW_UNI_DENSE) {
-                        const float wu = __int_as_float(hd.y);
-                        const int4 *po = reinterpret_cast<const int4 *>(st + F_WIN) + half * (F_GW / 4);
-#pragma unroll
-                        for (int q = 0; q < F_GW / 4; q++) {
-                            const int4 o = po[q];
-                            const float *s0 = st + o.x + ts, *s1 = st + o.y + ts, *s2 = st + o.z + ts, *s3 = st + o.w + ts;
-#pragma unroll
-                            for (int r = 0; r < F_R; r++) acc[4 * q][r] = fmaf(wu, s0[F_LANES * r], acc[4 * q][r]);
-#pragma unroll
-                            for (int r = 0; r < F_R; r++) acc[4 * q + 1][r] = fmaf(wu, s1[F_LANES * r], acc[4 * q + 1][r]);
-#pragma unroll
-                            for (int r = 0; r < F_R; r++) acc[4 * q + 2][r] = fmaf(wu, s2[F_LANES * r], acc[4 * q + 2][r]);
-#pragma unroll
-                            for (int r = 0; r < F_R; r++) acc[4 * q + 3][r] = fmaf(wu, s3[F_LANES * r], acc[4 * q + 3][r]);
-                        }
-                    } else if (kind == F_ROW_UNI_SPARSE) {
-                        const float wu = __int_as_float(hd.y);
-                        const unsigned mask = (unsigned)hd.z >> (half * F_GW);
-                        const int *po = reinterpret_cast<const int *>(st + F_WIN) + half * F_GW;
-#pragma unroll
-                        for (int a = 0; a < F_GW; a++) {
-                            if ((mask >> a) & 1u) {
-                                const float *s0 = st + po[a] + ts;
-#pragma unroll
-                                for (int r = 0; r < F_R; r++) acc[a][r] = fmaf(wu, s0[F_LANES * r], acc[a][r]);
-                            }
-                        }
-                    } else if (kind == F_ROW_DENSE) {
+                    if (kind == F_ROW_DENSE) {
 #pragma unroll
                         for (int q = 0; q < F_GW / 2; q++) {
                             const int4 v = pk4[q];
