@@ -30,6 +30,12 @@ int bpmf_standardize_envelopes(const float *envelopes, size_t n_stations, size_t
 int bpmf_saturated_envelopes(const float *traces, size_t n_stations, size_t n_components, size_t n_samples,
                              float anomaly_threshold, float max_dynamic_range, float *features,
                              int *data_availability);
+/* The same with every pointer in device memory (d_features may alias d_traces), enqueued on `stream` (a cudaStream_t
+ * passed as void*; synchronised once before returning): a day of traces that is already on the GPU -- the
+ * backprojection that consumes the features is -- does not make a round trip through host memory. */
+int bpmf_saturated_envelopes_dev(const float *d_traces, size_t n_stations, size_t n_components, size_t n_samples,
+                                 float anomaly_threshold, float max_dynamic_range, float *d_features,
+                                 int *d_data_availability, void *stream);
 
 /* BPMF/template_search.py:1418-1487 time_dependent_threshold (backprojection): windows i = 1..n_windows of
  * `window` samples every `shift` = int((1 - overlap) * window) samples, median + cnr_threshold * MAD per window

@@ -368,6 +368,25 @@ extern "C" int bpmf_saturated_envelopes(const float *traces, size_t n_stations, 
     return BPMF_OK;
 }
 
+// Device-resident form: traces, features and data_availability are device pointers, work is enqueued on `stream`
+// (the call synchronises that stream once before returning: its scratch buffers are freed on return).
+// d_features may alias d_traces.
+extern "C" int bpmf_saturated_envelopes_dev(const float *d_traces, size_t n_stations, size_t n_components,
+                                            size_t n_samples, float anomaly_threshold, float max_dynamic_range,
+                                            float *d_features, int *d_data_availability, void *stream) {
+    const size_t rows = n_stations * n_components, N = n_samples;
+    if (rows == 0 || N == 0) return BPMF_OK;
+    DevBuf env, spec, full;
+    BPMF_CUDA(env.alloc(sizeof(float) * rows * N));
+    BPMF_CUDA(spec.alloc(sizeof(cufftComplex) * (N / 2 + 1)));
+    BPMF_CUDA(full.alloc(sizeof(cufftComplex) * N));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = envelope_rows(d_traces, rows, N, spec.as<cufftComplex>(), full.as<cufftComplex>(), env.as<float>(), st);
+    if (rc != BPMF_OK) return rc;
+    return standardize_rows(env.as<float>(), n_stations, n_components, N, anomaly_threshold, max_dynamic_range,
+                            d_features, d_data_availability, st);
+}
+
 extern "C" int bpmf_bp_time_dependent_threshold(const float *network_response, size_t n_samples, size_t window,
                                                 size_t shift, float cnr_threshold, double *threshold) {
     const size_t n = n_samples;

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "bpmf_envelope": (C.c_int, [fp, z, z, fp]),
     "bpmf_standardize_envelopes": (C.c_int, [fp, z, z, z, C.c_float, C.c_float, fp, C.POINTER(C.c_int)]),
     "bpmf_saturated_envelopes": (C.c_int, [fp, z, z, z, C.c_float, C.c_float, fp, C.POINTER(C.c_int)]),
+    "bpmf_saturated_envelopes_dev": (C.c_int, [C.c_void_p, z, z, z, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                               C.c_void_p]),
     "bpmf_bp_time_dependent_threshold": (C.c_int, [fp, z, z, z, C.c_float, C.POINTER(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -85,6 +87,22 @@ def saturated_envelopes(traces, anomaly_threshold=1.0e-11, max_dynamic_range=1.0
         _check(lib.bpmf_saturated_envelopes(x.ctypes.data_as(fp), S, Cc, N, anomaly_threshold, max_dynamic_range,
                                             out.ctypes.data_as(fp), avail.ctypes.data_as(C.POINTER(C.c_int))),
                "bpmf_saturated_envelopes")
+    return out, avail
+
+
+def saturated_envelopes_dev(traces, anomaly_threshold=1.0e-11, max_dynamic_range=1.0e5):
+    """``saturated_envelopes`` on a float32 CUDA tensor ``(S, C, N)``: returns ``(features (S, C, N) float32,
+    data_availability (S,) int32)`` as CUDA tensors, nothing crosses PCIe."""
+    import torch
+
+    lib = load()
+    assert traces.is_cuda and traces.dtype == torch.float32 and traces.dim() == 3 and traces.is_contiguous()
+    S, Cc, N = traces.shape
+    out = torch.empty_like(traces)
+    avail = torch.zeros(S, dtype=torch.int32, device=traces.device)
+    _check(lib.bpmf_saturated_envelopes_dev(traces.data_ptr(), S, Cc, N, float(anomaly_threshold),
+                                            float(max_dynamic_range), out.data_ptr(), avail.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "bpmf_saturated_envelopes_dev")
     return out, avail
 
 

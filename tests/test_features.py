@@ -104,3 +104,17 @@ def test_backprojection_threshold_vs_reference_vectors(golden):
         want = golden["thr_%s_out" % tag]
         assert thr.dtype == np.float64 and thr.shape == want.shape
         assert np.abs(thr - want).max() <= 1e-9 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+def test_saturated_envelopes_device_form_matches_host_form():
+    import torch
+
+    from seismic_bpmf_b200 import features as ft
+
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal((3, 2, 60750)) * 1e-6).astype(np.float32)
+    x[1, 0, 1000:9000] = 0.0
+    want, avail = ft.saturated_envelopes(x)
+    got, avail_d = ft.saturated_envelopes_dev(torch.from_numpy(x).cuda())
+    assert np.array_equal(got.cpu().numpy(), want) and np.array_equal(avail_d.cpu().numpy(), avail)

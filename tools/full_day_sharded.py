@@ -98,9 +98,7 @@ def main():
     # ---------------------------------------------------------------- 1. detection traces
     t0 = time.perf_counter()
     t_all = t0
-    traces_h = traces.cpu().numpy()
-    feat_h, avail = features.saturated_envelopes(traces_h)
-    feat = torch.from_numpy(feat_h).to(dev)
+    feat, avail = features.saturated_envelopes_dev(traces)  # the day is already on the device
     t0 = stage("detection_traces_s", t0)
     # ---------------------------------------------------------------- 2. moveout table (int32 samples, relative to first)
     mv_h, m2t = template_search.moveouts_from_travel_times(tt.cpu().numpy(), sr, relative_to_first=True)
