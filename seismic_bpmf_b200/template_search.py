@@ -43,6 +43,30 @@ def moveouts_from_travel_times(travel_times, sampling_rate, relative_to_first=Tr
     return mv, m2t
 
 
+def moveouts_from_travel_times_dev(travel_times, sampling_rate, relative_to_first=True, epsilon=0.2):
+    """The same on a float32 / float64 CUDA tensor ``(K, S, P)``: returns ``(moveouts int32 (K, S, P), moveout_to_tt
+    float64 (K,))`` as CUDA tensors (what ``device.BeamformPlan`` / ``sharded.beamform_max_sharded`` take); the table
+    never visits the host.  Raises if a moveout does not fit int32."""
+    import torch
+
+    lib = _lib.load()
+    tt = travel_times
+    assert tt.is_cuda and tt.dim() == 3 and tt.is_contiguous() and tt.dtype in (torch.float32, torch.float64)
+    K, S, P = tt.shape
+    mv = torch.empty((K, S, P), dtype=torch.int32, device=tt.device)
+    m2t = torch.zeros(K, dtype=torch.float64, device=tt.device)
+    overflow = torch.zeros(1, dtype=torch.int32, device=tt.device)
+    if tt.numel():
+        rc = lib.bpmf_moveouts_from_travel_times_dev(
+            tt.data_ptr(), 1 if tt.dtype == torch.float64 else 0, K, S, P, float(sampling_rate), float(epsilon),
+            1 if relative_to_first else 0, mv.data_ptr(), m2t.data_ptr(), overflow.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "bpmf_moveouts_from_travel_times_dev")
+        if int(overflow.item()):
+            raise _lib.BpmfError("moveouts_from_travel_times_dev: a moveout exceeds the int32 range")
+    return mv, m2t
+
+
 class MoveoutTable:
     """Cached moveouts of a travel-time table, keyed like ``get_travel_times_array`` is called.
 

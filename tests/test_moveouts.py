@@ -69,3 +69,17 @@ def test_kernel_matches_oracle_large_and_table_cache():
     assert np.array_equal(sub, mo.moveouts_from_travel_times(tt[:, [2, 0]][:, :, [1]], 50.0)[0])
     dev = table.device_moveouts()
     assert dev.is_cuda and dev.dtype.is_floating_point is False and np.array_equal(dev.cpu().numpy(), mv)
+
+
+@pytest.mark.gpu
+def test_device_resident_table_matches_host_form():
+    import torch
+
+    from seismic_bpmf_b200 import template_search as ts
+
+    rng = np.random.default_rng(8)
+    for dtype in (np.float32, np.float64):
+        tt = rng.uniform(0.0, 60.0, (5000, 7, 2)).astype(dtype)
+        mv, m2t = ts.moveouts_from_travel_times(tt, 100.0)
+        mv_d, m2t_d = ts.moveouts_from_travel_times_dev(torch.from_numpy(tt).cuda(), 100.0)
+        assert np.array_equal(mv_d.cpu().numpy(), mv) and np.array_equal(m2t_d.cpu().numpy(), m2t)

@@ -101,8 +101,7 @@ def main():
     feat, avail = features.saturated_envelopes_dev(traces)  # the day is already on the device
     t0 = stage("detection_traces_s", t0)
     # ---------------------------------------------------------------- 2. moveout table (int32 samples, relative to first)
-    mv_h, m2t = template_search.moveouts_from_travel_times(tt.cpu().numpy(), sr, relative_to_first=True)
-    mv_bp = torch.from_numpy(mv_h).to(dev)
+    mv_bp, m2t = template_search.moveouts_from_travel_times_dev(tt, sr, relative_to_first=True)
     t0 = stage("moveout_table_s", t0)
     # ---------------------------------------------------------------- 3. backprojection, source-sharded
     wp = torch.zeros((S, Cc, 2), device=dev)
@@ -115,7 +114,7 @@ def main():
     # ---------------------------------------------------------------- 4. threshold + picks (replicated, small)
     mb_h, am_h = maxbeam.cpu().numpy(), argmax.cpu().numpy()
     thr = features.time_dependent_threshold(mb_h, int(1800 * sr), overlap=0.75, CNR_threshold=10.0)
-    search_win = int(mv_h.max()) + 1
+    search_win = int(mv_bp.max().item()) + 1
     picks = np.flatnonzero(clib.select_cc_indexes(mb_h, np.float32(thr), search_win))
     if len(picks) > a.max_templates:  # keep the strongest
         keep = np.argsort(mb_h[picks])[::-1][: a.max_templates]
