@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                     const int dense = __popc(nz) > F_G / 2;
                     if (lane < F_G)
                         reinterpret_cast<int2 *>(st + F_WIN)[lane] =
-                            (b != 0.f) ? make_int2((int)((long long)tv - wlo), __float_as_int(b))
-                                       : make_int2((int)(zero_s - st), 0);
+                            (b != 0.f) ? make_int2(4 * (int)((long long)tv - wlo), __float_as_int(b))
+                                       : make_int2(4 * (int)(zero_s - st), 0);  // BYTE offsets: one add per gather address
                     if (lane == 0) hdr[0] = dense ? F_ROW_DENSE : F_ROW_SPARSE;
                     // samples [g0, g0 + len) of the row are needed; the part outside [0, pitch) reads as zero
                     const long long g0 = t0 + wlo;                                      // multiple of 4
@@ -566,12 +566,14 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                     const int kind = reinterpret_cast<const int *>(st + F_WIN + 2 * F_G)[0];
                     // (offset, weight) of this warp's positions 2q, 2q + 1
                     const int4 *pk4 = reinterpret_cast<const int4 *>(st + F_WIN) + half * (F_GW / 2);
+                    const char *sb = reinterpret_cast<const char *>(st + ts);  // this thread's first sample of the window
                     if (kind == F_ROW_DENSE) {
 #pragma unroll
                         for (int q = 0; q < F_GW / 2; q++) {
                             const int4 v = pk4[q];
                             const float b0 = __int_as_float(v.y), b1 = __int_as_float(v.w);
-                            const float *s0 = st + v.x + ts, *s1 = st + v.z + ts;
+                            const float *s0 = reinterpret_cast<const float *>(sb + v.x);
+                            const float *s1 = reinterpret_cast<const float *>(sb + v.z);
 #pragma unroll
                             for (int r = 0; r < F_R; r++) acc[2 * q][r] = fmaf(b0, s0[F_LANES * r], acc[2 * q][r]);
 #pragma unroll
@@ -583,12 +585,12 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                             const int4 v = pk4[q];
                             const float b0 = __int_as_float(v.y), b1 = __int_as_float(v.w);
                             if (b0 != 0.f) {
-                                const float *s0 = st + v.x + ts;
+                                const float *s0 = reinterpret_cast<const float *>(sb + v.x);
 #pragma unroll
                                 for (int r = 0; r < F_R; r++) acc[2 * q][r] = fmaf(b0, s0[F_LANES * r], acc[2 * q][r]);
                             }
                             if (b1 != 0.f) {
-                                const float *s1 = st + v.z + ts;
+                                const float *s1 = reinterpret_cast<const float *>(sb + v.z);
 #pragma unroll
                                 for (int r = 0; r < F_R; r++) acc[2 * q + 1][r] = fmaf(b1, s1[F_LANES * r], acc[2 * q + 1][r]);
                             }
