@@ -283,23 +283,52 @@ __global__ void __launch_bounds__(B_THREADS, 2)
 // give groups of 16; unrelated moveouts degrade to groups of one source, never to a different code path.
 //   beam_pack_kernel : warp per super-block -> transposed moveouts tauT[sb][sp][16], weights
 //                      betaT[sb][s][16] and the group list grp[sb][16] (start | count << 8, 0 = end).
-//   beam_group_kernel: CTA = 768-sample time tile x a range of super-blocks.  One PRODUCER warp walks
-//                      (group, row): window start = min moveout of the group, (offset, weight) table of
-//                      the row, one cp.async.bulk (TMA) of the <= 5 KB row window into a ring of
-//                      F_NSTAGE stages, completion on the stage's "full" mbarrier.  Eight CONSUMER warps
-//                      (16 sources x 3 samples of register accumulators per thread, lanes = consecutive
+//   beam_group_kernel: CTA = 2688-sample time tile x a range of super-blocks, ONE CTA per SM.  One PRODUCER
+//                      warp walks (group, row): window start = min moveout of the group, (offset, weight)
+//                      table of the row, one cp.async.bulk (TMA) of the <= 12.5 KB row window into a ring of
+//                      F_NSTAGE stages, completion on the stage's "full" mbarrier.  Twelve CONSUMER warps
+//                      (8 sources x 14 samples of register accumulators per thread, lanes = consecutive
 //                      samples: conflict-free 4-byte LDS per gather-FMA) wait on "full", accumulate,
 //                      and release the stage on its "empty" mbarrier -- no CTA-wide barrier, warps drift.
-constexpr int F_CONS_WARPS = 8;
+// Tile shape (r2 sweeps, gpurun r2s25-r2s35; bench grid, dense / 10-closest weighting, ms per pass):
+//   3 samples x 8 warps x 2 CTAs/SM (r1)        269 / 126      6 x 10 warps, 1 CTA/SM              208 / 92
+//   10 x 8 warps, setmaxnreg 232                196 / 73.5     + 2 warps share the samples (SPLIT 2) 191 / 73.5
+//   + unused rows skipped 32 at a time, valid ranges in the terminator, running max in shared memory,
+//     7 x 12 warps, setmaxnreg 152 (this file)  189 / 60
+// The loop is bound by the gathers in flight: ptxas keeps a sliding window of ~11 loads ahead of the first FMA
+// and issue is in order, so the warps (12 x 11 loads) have to cover the shared-memory latency under load; the
+// samples per thread amortise the row hand-shake (wait -> header -> table -> first gather, ~120 cycles) and the
+// 8 table wavefronts of the row.  Both are bought with registers, hence one CTA per SM and setmaxnreg.
+#ifndef BEAM_CONS_WARPS
+#define BEAM_CONS_WARPS 12
+#endif
+constexpr int F_CONS_WARPS = BEAM_CONS_WARPS;
 constexpr int F_CONS = 32 * F_CONS_WARPS;        // consumer threads
-constexpr int F_THREADS = F_CONS + 32;           // + the producer warp
+// BEAM_CONS_REGS != 0: the producer sits in a warpgroup of its own (its three other warps leave at once) and hands
+// its registers to the three consumer warpgroups (setmaxnreg): 128 registers per thread at launch (512 threads, one
+// CTA per SM), then 40 for the producer warpgroup and 152 for the consumers -- 112 accumulators + gathers in flight.
+#ifndef BEAM_CONS_REGS
+#define BEAM_CONS_REGS 152
+#endif
+#ifndef BEAM_PROD_REGS
+#define BEAM_PROD_REGS 40
+#endif
+constexpr int F_THREADS = F_CONS + (BEAM_CONS_REGS ? 128 : 32);  // + the producer warp (warpgroup)
+static_assert(!BEAM_CONS_REGS || F_CONS_WARPS % 4 == 0, "setmaxnreg works on whole warpgroups");
 // SPLIT (template parameter of the kernel) = consumer warps that share the samples of a group, each taking
-// 16 / SPLIT of its sources and 3 * SPLIT samples per thread: always 48 accumulators, which leave room, inside the
-// 96 registers that let two CTAs share an SM, for gathers in flight.  SPLIT = 1 is 2 % faster on fully weighted
-// rows, SPLIT = 2 is 8 % faster when many (source, station) pairs have zero weight (fewer table loads and
-// branches per warp); beam_pack_kernel counts the pairs and the two instantiations decide on the device.
-constexpr int F_TT = F_CONS * 3;                 // 768-sample tile
+// 16 / SPLIT of its sources and BEAM_SPT * SPLIT samples per thread: always 16 * BEAM_SPT accumulators.  SPLIT = 2
+// (half the table loads per gather) is the default; BPMF_BEAM_SPLIT=1 selects the other instantiation for A/B runs.
+#ifndef BEAM_SPT
+#define BEAM_SPT 7                               // samples per consumer thread (x SPLIT): 112 accumulators
+#endif
+#ifndef BEAM_MINB
+#define BEAM_MINB 1                              // CTAs per SM the register budget is sized for
+#endif
+constexpr int F_TT = F_CONS * BEAM_SPT;          // 2688-sample tile
 constexpr int F_G = 16;                          // sources per super-block / largest group
+#ifndef BEAM_DENSE_MIN
+#define BEAM_DENSE_MIN 8                         // rows with more weighted positions than this run the straight-line code
+#endif
 #ifndef BEAM_MARGIN
 #define BEAM_MARGIN 512
 #endif
@@ -318,7 +347,7 @@ __global__ void __launch_bounds__(128)
     beam_pack_kernel(const int *__restrict__ tau, const float *__restrict__ beta, size_t K, int S, int P,
                      int *__restrict__ tauT, float *__restrict__ betaT, unsigned short *__restrict__ grp,
                      int *__restrict__ dlist, int *__restrict__ dcount) {
-    // dcount[0]: sources listed for the direct kernel; dcount[1], dcount[2]: weighted / unweighted (source, station) pairs
+    // dcount[0]: sources listed for the direct kernel
     extern __shared__ long long pack_sm[];  // per warp: mn[SP], mx[SP]
     const int SP = S * P;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -333,22 +362,9 @@ __global__ void __launch_bounds__(128)
         const int j = e / SP, sp = e - j * SP;
         tauT[(sb * SP + sp) * F_G + j] = (j < nk) ? tau[(k0 + j) * SP + sp] : 0;
     }
-    int n_w = 0, n_z = 0;
     for (int e = lane; e < F_G * S; e += 32) {
         const int j = e / S, s = e - j * S;
-        const float b = (j < nk) ? beta[(k0 + j) * S + s] : 0.f;
-        betaT[(sb * S + s) * F_G + j] = b;
-        if (j < nk) { if (b != 0.f) n_w++; else n_z++; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_w += __shfl_xor_sync(0xffffffffu, n_w, o);
-        n_z += __shfl_xor_sync(0xffffffffu, n_z, o);
-    }
-    if (lane == 0) {
-        // saturating counters are enough: only the ratio matters
-        if (n_w) atomicAdd(dcount + 1, n_w);
-        if (n_z) atomicAdd(dcount + 2, n_z);
+        betaT[(sb * S + s) * F_G + j] = (j < nk) ? beta[(k0 + j) * S + s] : 0.f;
     }
     // greedy grouping
     for (int sp = lane; sp < SP; sp += 32) { mn_s[sp] = LLONG_MAX; mx_s[sp] = LLONG_MIN; }
@@ -390,30 +406,39 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-// Two CTAs of 9 warps per SM: the register file is split over the four SM sub-partitions (16 384 registers
-// each), a sub-partition then hosts up to five of the 18 warps, so a thread may hold 96 registers.
-//
 // Record stream producer -> consumers (one record per stage): a record is one (station, phase) row that at
 // least one member of the group uses -- rows nobody uses are never emitted -- and every group ends with a
 // terminator record.  Record kinds: F_ROW_DENSE (straight-line code over the 16 positions; positions without
 // weight point at a block of zeros with weight 0, so that fmaf(0, 0, acc) leaves acc untouched whatever the
-// row holds), F_ROW_SPARSE (at most half of the positions weighted: warp-uniform branches), F_END.
+// row holds), F_ROW_SPARSE (at most half of the positions weighted: warp-uniform branches), F_END / F_END_INSIDE.
+// The terminator carries, per source of the group, the range of tile samples that are valid for it (strict mode:
+// every station's window inside the data; read from tlo / thi by the producer, which runs ahead, instead of
+// sixteen dependent global loads in every consumer at the end of every group); F_END_INSIDE = every sample of the
+// tile is valid for every source, the consumers skip the range tests.
 // Groups of one or two sources (unrelated moveouts) are not worth a staged window: beam_pack_kernel lists
 // their sources and beam_direct_kernel gathers them straight from the L2-resident rows (4 B per gather-FMA
 // either way, without the per-row hand-shake); both kernels merge into the same (max, argmax) keys.
-constexpr int F_ROW_DENSE = 0, F_ROW_SPARSE = 2, F_END = 1;
+#ifdef BEAM_DIAG
+// diagnostic build only (tools/gpu scripts): cycles spent waiting, summed over CTAs
+//   [0] producer: waiting for a free stage   [1] producer: waiting for super-block parameters   [2] producer: total
+//   [3] consumer warp 0: waiting for a full stage   [4] consumer warp 0: group epilogues   [5] consumer warp 0: total
+//   [6] records   [7] groups
+__device__ unsigned long long beam_diag[8];
+#define DIAG_T0(v) const long long v = clock64()
+#define DIAG_ADD(acc, v) acc += clock64() - v
+#else
+#define DIAG_T0(v)
+#define DIAG_ADD(acc, v)
+#endif
+constexpr int F_ROW_DENSE = 0, F_ROW_SPARSE = 2, F_END = 1, F_END_INSIDE = 3;  // bit 0: terminator
 
 template <bool REDUCE_MAX, int SPLIT>
-__global__ void __launch_bounds__(F_THREADS, 2)
+__global__ void __launch_bounds__(F_THREADS, BEAM_MINB)
     beam_group_kernel(const float *__restrict__ U, const int *__restrict__ tauT, const float *__restrict__ betaT,
-                      const unsigned short *__restrict__ grp, const int *__restrict__ pair_count, const int *__restrict__ tlo,
+                      const unsigned short *__restrict__ grp, const int *__restrict__ tlo,
                       const int *__restrict__ thi, size_t K, int S, int P, long long N, long long pitch, int strict,
                       size_t sb_chunk, unsigned long long *__restrict__ keys, float *__restrict__ beam) {
-    constexpr int F_R = 3 * SPLIT, F_LANES = F_CONS / SPLIT, F_GW = F_G / SPLIT;
-    {   // pair_count = {weighted, unweighted} (source, station) pairs: the other instantiation takes the call
-        const bool sparse = 4ll * pair_count[1] > (long long)pair_count[0] + pair_count[1];
-        if (sparse != (SPLIT == 2)) return;
-    }
+    constexpr int F_R = BEAM_SPT * SPLIT, F_LANES = F_CONS / SPLIT, F_GW = F_G / SPLIT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int SP = S * P;
     float *stages = reinterpret_cast<float *>(smem_raw);                        // F_NSTAGE x F_STAGE
@@ -422,6 +447,8 @@ __global__ void __launch_bounds__(F_THREADS, 2)
     float *par_beta = reinterpret_cast<float *>(par_tau + 2 * SP * F_G);        // 2 x S x 16
     uint64_t *bars = reinterpret_cast<uint64_t *>(par_beta + 2 * S * F_G);
     uint64_t *full = bars, *empty = bars + F_NSTAGE, *pfull = bars + 2 * F_NSTAGE;  // [F_NSTAGE], [F_NSTAGE], [2]
+    float *best_s = reinterpret_cast<float *>(bars + 2 * F_NSTAGE + 2);                // REDUCE_MAX: [F_R][F_CONS]
+    unsigned *bestk_s = reinterpret_cast<unsigned *>(best_s + F_R * F_CONS);           //             [F_R][F_CONS]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long t0 = (long long)blockIdx.x * F_TT;
@@ -440,11 +467,23 @@ __global__ void __launch_bounds__(F_THREADS, 2)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#if BEAM_CONS_REGS
+    if (warp >= F_CONS_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BEAM_PROD_REGS));
+        if (warp != F_CONS_WARPS) return;
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BEAM_CONS_REGS));
+    }
+#endif
 
     if (warp == F_CONS_WARPS) {
         // ===================== producer warp ==========================================================
         const uint32_t par_bytes = (uint32_t)(sizeof(int) * SP * F_G + sizeof(float) * S * F_G);
         uint32_t it = 0;
+#ifdef BEAM_DIAG
+        long long d_par = 0, d_empty = 0, d_groups = 0;
+        const long long d_start = clock64();
+#endif
         for (size_t sb = sb_begin; sb < sb_end; sb++) {
             const uint32_t u = (uint32_t)(sb - sb_begin);
             const int pb = u & 1;
@@ -463,7 +502,11 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                              (uint32_t)(sizeof(float) * S * F_G), pfull + (pb ^ 1));
                 }
             }
-            mbar_wait(pfull + pb, (u >> 1) & 1);
+            {
+                DIAG_T0(c0);
+                mbar_wait(pfull + pb, (u >> 1) & 1);
+                DIAG_ADD(d_par, c0);
+            }
             const int *tau_p = par_tau + pb * SP * F_G;
             const float *beta_p = par_beta + pb * S * F_G;
             for (int g = 0; g < F_G; g++) {
@@ -471,7 +514,25 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                 const int n = (int)(gd >> 8), j0 = (int)(gd & 0xffu);
                 if (n == 0) break;
                 if (n <= F_DIRECT_MAX) continue;  // left to beam_direct_kernel
-                for (int sp = 0; sp < SP; sp++) {
+                // valid samples of source j0 + lane, relative to the tile (used by the terminator record)
+                long long lo_k = 0, hi_k = N - 1;
+                if (strict && lane < n) {
+                    lo_k = tlo[sb * F_G + j0 + lane];
+                    hi_k = thi[sb * F_G + j0 + lane];
+                }
+                for (int sp0 = 0; sp0 < SP; sp0 += 32) {
+                  // rows sp0 .. sp0 + 31 that at least one member of the group uses (one lane per row); the others
+                  // are never emitted, and skipping them 32 at a time keeps the producer ahead of the consumers
+                  // when every source weights only a few stations
+                  bool used = false;
+                  if (sp0 + lane < SP) {
+                      const float *bp = beta_p + ((sp0 + lane) / P) * F_G + j0;
+                      for (int a = 0; a < n; a++) used |= bp[a] != 0.f;
+                  }
+                  unsigned row_mask = __ballot_sync(0xffffffffu, used);
+                  while (row_mask) {
+                    const int sp = sp0 + __ffs(row_mask) - 1;
+                    row_mask &= row_mask - 1;
                     const int s = sp / P;
                     // lane a < 16 owns position a of the group (source slot j0 + a)
                     float b = 0.f;
@@ -481,7 +542,6 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                         tv = tau_p[sp * F_G + j0 + lane];
                     }
                     const unsigned nz = __ballot_sync(0xffffffffu, b != 0.f);
-                    if (nz == 0u) continue;  // no member of the group uses this row: nothing is emitted
                     int mn = (b != 0.f) ? tv : INT_MAX, mx = (b != 0.f) ? tv : INT_MIN;
 #pragma unroll
                     for (int o = 8; o > 0; o >>= 1) {  // lanes 16-31 hold the neutral elements
@@ -492,12 +552,16 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                     mn = __shfl_sync(0xffffffffu, mn, 0);
                     mx = __shfl_sync(0xffffffffu, mx, 0);
                     const int stage = it % F_NSTAGE;
-                    mbar_wait(empty + stage, ((it / F_NSTAGE) & 1) ^ 1);
+                    {
+                        DIAG_T0(c0);
+                        mbar_wait(empty + stage, ((it / F_NSTAGE) & 1) ^ 1);
+                        DIAG_ADD(d_empty, c0);
+                    }
                     it++;
                     float *st = stages + stage * F_STAGE;
                     int *hdr = reinterpret_cast<int *>(st + F_WIN + 2 * F_G);
                     const long long wlo = align4_down((long long)mn);
-                    const int dense = __popc(nz) > F_G / 2;
+                    const int dense = __popc(nz) > BEAM_DENSE_MIN;
                     if (lane < F_G)
                         reinterpret_cast<int2 *>(st + F_WIN)[lane] =
                             (b != 0.f) ? make_int2(4 * (int)((long long)tv - wlo), __float_as_int(b))
@@ -523,29 +587,56 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                             mbar_arrive(full + stage);
                         }
                     }
+                  }
                 }
                 // terminator record of the group
                 const int stage = it % F_NSTAGE;
                 mbar_wait(empty + stage, ((it / F_NSTAGE) & 1) ^ 1);
                 it++;
-                if (lane == 0) {
-                    reinterpret_cast<int *>(stages + stage * F_STAGE + F_WIN + 2 * F_G)[0] = F_END;
-                    mbar_arrive(full + stage);
+                {
+                    float *st = stages + stage * F_STAGE;
+                    int lo_rel = F_TT, hi_rel = -1;  // positions beyond the group: empty range
+                    if (lane < n) {
+                        const long long a = lo_k - t0, b = hi_k - t0;
+                        lo_rel = (int)(a < 0 ? 0 : (a > F_TT ? F_TT : a));
+                        hi_rel = (int)(b < -1 ? -1 : (b > F_TT - 1 ? F_TT - 1 : b));
+                    }
+                    const bool inside = __all_sync(0xffffffffu, lane >= n || (lo_rel == 0 && hi_rel == F_TT - 1));
+                    if (lane < F_G) reinterpret_cast<int2 *>(st + F_WIN)[lane] = make_int2(lo_rel, hi_rel);
+                    if (lane == 0) reinterpret_cast<int *>(st + F_WIN + 2 * F_G)[0] = inside ? F_END_INSIDE : F_END;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full + stage);
                 }
+#ifdef BEAM_DIAG
+                d_groups++;
+#endif
             }
         }
+#ifdef BEAM_DIAG
+        if (lane == 0) {
+            atomicAdd(beam_diag + 0, (unsigned long long)d_empty);
+            atomicAdd(beam_diag + 1, (unsigned long long)d_par);
+            atomicAdd(beam_diag + 2, (unsigned long long)(clock64() - d_start));
+            atomicAdd(beam_diag + 6, (unsigned long long)it);
+            atomicAdd(beam_diag + 7, (unsigned long long)d_groups);
+        }
+#endif
     } else {
         // ===================== consumer warps =========================================================
         // warp w takes source positions [F_GW * (w % SPLIT), + F_GW) of every group and the samples
         // t0 + ts + F_LANES * r, ts = 32 * (w / SPLIT) + lane, r < F_R (lanes = consecutive samples)
         const int half = warp % SPLIT;
         const int ts = 32 * (warp / SPLIT) + lane;
-        float best[F_R];
-        unsigned bestk[F_R];
+        if (REDUCE_MAX) {
 #pragma unroll
-        for (int r = 0; r < F_R; r++) { best[r] = -INFINITY; bestk[r] = 0u; }
+            for (int r = 0; r < F_R; r++) { best_s[r * F_CONS + tid] = -INFINITY; bestk_s[r * F_CONS + tid] = 0u; }
+        }
         uint32_t it = 0;
         bool any = false;
+#ifdef BEAM_DIAG
+        long long d_full = 0, d_epi = 0;
+        const long long d_start = clock64();
+#endif
         for (size_t sb = sb_begin; sb < sb_end; sb++) {
             for (int g = 0; g < F_G; g++) {
                 const unsigned gd = grp[sb * F_G + g];
@@ -558,12 +649,18 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                 for (int a = 0; a < F_GW; a++)
 #pragma unroll
                     for (int r = 0; r < F_R; r++) acc[a][r] = 0.f;
+                int stage, kind;
+                const float *st;
                 for (;;) {
-                    const int stage = it % F_NSTAGE;
-                    mbar_wait(full + stage, (it / F_NSTAGE) & 1);
+                    stage = it % F_NSTAGE;
+                    {
+                        DIAG_T0(c0);
+                        mbar_wait(full + stage, (it / F_NSTAGE) & 1);
+                        DIAG_ADD(d_full, c0);
+                    }
                     it++;
-                    const float *st = stages + stage * F_STAGE;
-                    const int kind = reinterpret_cast<const int *>(st + F_WIN + 2 * F_G)[0];
+                    st = stages + stage * F_STAGE;
+                    kind = reinterpret_cast<const int *>(st + F_WIN + 2 * F_G)[0];
                     // (offset, weight) of this warp's positions 2q, 2q + 1
                     const int4 *pk4 = reinterpret_cast<const int4 *>(st + F_WIN) + half * (F_GW / 2);
                     const char *sb = reinterpret_cast<const char *>(st + ts);  // this thread's first sample of the window
@@ -596,38 +693,84 @@ __global__ void __launch_bounds__(F_THREADS, 2)
                             }
                         }
                     }
+                    if (kind & 1) break;  // terminator: released after the ranges have been read
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty + stage);
-                    if (kind == F_END) break;
                 }
-#pragma unroll
-                for (int a = 0; a < F_GW; a++) {
-                    const int pos = half * F_GW + a;
-                    if (pos < n) {
-                        const size_t k = sb * F_G + j0 + pos;
-                        long long lo_k = 0, hi_k = N - 1;
-                        if (strict) { lo_k = tlo[k]; hi_k = thi[k]; }
+                DIAG_T0(c_epi);
+                const int2 *rng = reinterpret_cast<const int2 *>(st + F_WIN) + half * F_GW;
+                const int na = n - half * F_GW;  // this warp's positions [0, na) hold sources of the group
+                if (REDUCE_MAX) {
+                    // running (max, argmax) of the thread's samples: in shared memory, read and written once per
+                    // group -- 2 * F_R registers less in the gather loop, i.e. more gathers in flight
+                    const unsigned kbase = (unsigned)(sb * F_G + j0 + half * F_GW);
+                    if (kind == F_END_INSIDE) {  // every sample of the tile is valid for every source of the group
 #pragma unroll
                         for (int r = 0; r < F_R; r++) {
-                            const long long t = t0 + ts + F_LANES * r;
-                            const float v = (t >= lo_k && t <= hi_k) ? acc[a][r] : 0.f;
-                            if (REDUCE_MAX) {
-                                if (v > best[r]) { best[r] = v; bestk[r] = (unsigned)k; }
-                            } else if (t < N) {
-                                beam[k * (size_t)N + (size_t)t] = v;
+                            float bv = best_s[r * F_CONS + tid];
+                            int win = -1;
+#pragma unroll
+                            for (int a = 0; a < F_GW; a++)
+                                if (a < na && acc[a][r] > bv) { bv = acc[a][r]; win = a; }
+                            if (win >= 0) {
+                                best_s[r * F_CONS + tid] = bv;
+                                bestk_s[r * F_CONS + tid] = kbase + (unsigned)win;
+                            }
+                        }
+                    } else {
+                        int2 rg[F_GW];
+#pragma unroll
+                        for (int a = 0; a < F_GW; a++) rg[a] = rng[a];
+#pragma unroll
+                        for (int r = 0; r < F_R; r++) {
+                            const int trel = ts + F_LANES * r;
+                            float bv = best_s[r * F_CONS + tid];
+                            int win = -1;
+#pragma unroll
+                            for (int a = 0; a < F_GW; a++) {
+                                const float v = (trel >= rg[a].x && trel <= rg[a].y) ? acc[a][r] : 0.f;
+                                if (a < na && v > bv) { bv = v; win = a; }
+                            }
+                            if (win >= 0) {
+                                best_s[r * F_CONS + tid] = bv;
+                                bestk_s[r * F_CONS + tid] = kbase + (unsigned)win;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < F_GW; a++) {
+                        if (a < na) {
+                            const size_t k = sb * F_G + j0 + half * F_GW + a;
+                            const int2 rg = rng[a];
+#pragma unroll
+                            for (int r = 0; r < F_R; r++) {
+                                const int trel = ts + F_LANES * r;
+                                const float v = (trel >= rg.x && trel <= rg.y) ? acc[a][r] : 0.f;
+                                if (t0 + trel < N) beam[k * (size_t)N + (size_t)(t0 + trel)] = v;
                             }
                         }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                DIAG_ADD(d_epi, c_epi);
             }
         }
+#ifdef BEAM_DIAG
+        if (tid == 0) {
+            atomicAdd(beam_diag + 3, (unsigned long long)d_full);
+            atomicAdd(beam_diag + 4, (unsigned long long)d_epi);
+            atomicAdd(beam_diag + 5, (unsigned long long)(clock64() - d_start));
+        }
+#endif
         if (REDUCE_MAX && any) {
 #pragma unroll
             for (int r = 0; r < F_R; r++) {
                 const long long t = t0 + ts + F_LANES * r;
                 if (t < N) {
-                    const unsigned long long key =
-                        ((unsigned long long)ordered_bits(best[r]) << 32) | (unsigned long long)(~bestk[r]);
+                    const unsigned long long key = ((unsigned long long)ordered_bits(best_s[r * F_CONS + tid]) << 32) |
+                                                   (unsigned long long)(~bestk_s[r * F_CONS + tid]);
                     atomicMax(keys + t, key);
                 }
             }
@@ -727,9 +870,9 @@ __global__ void __launch_bounds__(D_THREADS)
     }
 }
 
-static size_t beam_group_smem_bytes(size_t S, size_t P) {
+static size_t beam_group_smem_bytes(size_t S, size_t P, bool reduce_max, int split) {
     return sizeof(float) * (F_NSTAGE * F_STAGE + F_TT) + 2 * (sizeof(int) * S * P * F_G + sizeof(float) * S * F_G) +
-           sizeof(uint64_t) * (2 * F_NSTAGE + 2);
+           sizeof(uint64_t) * (2 * F_NSTAGE + 2) + (reduce_max ? 2 * sizeof(float) * F_TT * (size_t)split : 0);
 }
 
 __global__ void beam_finalize_kernel(const unsigned long long *__restrict__ keys, size_t N,
@@ -786,6 +929,25 @@ static BeamWs carve(Workspace &ws, size_t K, size_t S, size_t P, size_t N) {
     return b;
 }
 
+#ifndef BEAM_SPLIT_DEFAULT
+#define BEAM_SPLIT_DEFAULT 2
+#endif
+
+template <bool REDUCE_MAX, int SPLIT, typename... Args>
+static int launch_group_split(dim3 grid, size_t smem, cudaStream_t st, Args... args) {
+    BPMF_CUDA(cudaFuncSetAttribute(beam_group_kernel<REDUCE_MAX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    beam_group_kernel<REDUCE_MAX, SPLIT><<<grid, F_THREADS, smem, st>>>(args...);
+    BPMF_LAUNCH_CHECK();
+    return BPMF_OK;
+}
+
+template <bool REDUCE_MAX, typename... Args>
+static int launch_group(int split, dim3 grid, size_t smem, cudaStream_t st, Args... args) {
+    if (split == 1) return launch_group_split<REDUCE_MAX, 1>(grid, smem, st, args...);
+    return launch_group_split<REDUCE_MAX, 2>(grid, smem, st, args...);
+}
+
 static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, const float *d_wp,
                     const float *d_beta, size_t K, size_t S, size_t C, size_t P, size_t N,
                     int flexible, int source_offset, void *d_ws, size_t ws_bytes, float *d_max,
@@ -809,15 +971,18 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
             d_tau, d_beta, K, (int)S, (int)P, (long long)N, b.tlo, b.thi);
         BPMF_LAUNCH_CHECK();
     }
-    // grouped warp-specialised kernel unless its shared-memory footprint rules out two CTAs per SM
+    // grouped warp-specialised kernel unless its shared-memory footprint does not fit the SM
     // (hundreds of stations) or BPMF_BEAM_KERNEL=legacy asks for the barrier-synchronised one
-    const size_t gsmem = beam_group_smem_bytes(S, P);
-    bool grouped = gsmem <= 110 * 1024;
+    int split = BEAM_SPLIT_DEFAULT;  // consumer warps per group of samples (BPMF_BEAM_SPLIT = 1 / 2 for A/B runs)
+    if (const char *e = getenv("BPMF_BEAM_SPLIT")) split = atoi(e);
+    split = split == 1 ? 1 : 2;
+    const size_t gsmem = beam_group_smem_bytes(S, P, reduce_max, split);
+    bool grouped = gsmem <= (size_t)(226 * 1024) / BEAM_MINB - 1024;  // BEAM_MINB CTAs per SM (1 KB reserved each)
     if (const char *e = getenv("BPMF_BEAM_KERNEL")) grouped = grouped && strcmp(e, "legacy") != 0;
     const size_t n_sb = (K + F_G - 1) / F_G;
     if (grouped && K > 0) {
         const int warps = 4;
-        BPMF_CUDA(cudaMemsetAsync(b.dcount, 0, 3 * sizeof(int), st));
+        BPMF_CUDA(cudaMemsetAsync(b.dcount, 0, sizeof(int), st));
         beam_pack_kernel<<<(unsigned)((n_sb + warps - 1) / warps), warps * 32,
                            sizeof(long long) * 2 * S * P * warps, st>>>(d_tau, d_beta, K, (int)S, (int)P, b.tauT,
                                                                          b.betaT, b.grp, b.dlist, b.dcount);
@@ -836,24 +1001,26 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
             const size_t want = (size_t)num_sms() * 4;
             size_t n_chunks = (n_tiles >= want) ? 1 : (want + n_tiles - 1) / n_tiles;
             if (grouped) {
+                // CTAs run in waves of (SMs x BEAM_MINB); a short time axis gives only a few waves, so the source
+                // chunking is chosen to leave the last wave as full as possible (4.56 waves -> 91 % of the machine)
+                const size_t slots = (size_t)num_sms() * BEAM_MINB;
+                if (n_tiles < 16 * slots) {
+                    const size_t c_lo = std::max<size_t>(1, (4 * slots + n_tiles - 1) / n_tiles);
+                    const size_t c_hi = std::max<size_t>(c_lo, (12 * slots + n_tiles - 1) / n_tiles);
+                    double best_eff = -1.0;
+                    for (size_t c = c_lo; c <= c_hi && c <= n_sb; c++) {
+                        const size_t sbc = (n_sb + c - 1) / c, cc = (n_sb + sbc - 1) / sbc;
+                        const size_t items = n_tiles * cc, waves = (items + slots - 1) / slots;
+                        const double eff = (double)items / (double)(waves * slots);
+                        if (eff > best_eff + 1e-3) { best_eff = eff; n_chunks = cc; }
+                    }
+                }
                 size_t sb_chunk = (n_sb + n_chunks - 1) / n_chunks;
                 n_chunks = (n_sb + sb_chunk - 1) / sb_chunk;
                 BPMF_REQUIRE(n_chunks <= 65535, "beamform: too many source chunks");
-                BPMF_CUDA(cudaFuncSetAttribute(beam_group_kernel<true, 1>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-                BPMF_CUDA(cudaFuncSetAttribute(beam_group_kernel<true, 2>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-                dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
-                // both instantiations are launched; the one that does not match the weight sparsity counted by
-                // beam_pack_kernel returns at once
-                beam_group_kernel<true, 1><<<grid, F_THREADS, gsmem, st>>>(
-                    b.U, b.tauT, b.betaT, b.grp, b.dcount + 1, b.tlo, b.thi, K, (int)S, (int)P, (long long)N,
-                    (long long)pitch, flexible ? 0 : 1, sb_chunk, b.keys, nullptr);
-                BPMF_LAUNCH_CHECK();
-                beam_group_kernel<true, 2><<<grid, F_THREADS, gsmem, st>>>(
-                    b.U, b.tauT, b.betaT, b.grp, b.dcount + 1, b.tlo, b.thi, K, (int)S, (int)P, (long long)N,
-                    (long long)pitch, flexible ? 0 : 1, sb_chunk, b.keys, nullptr);
-                BPMF_LAUNCH_CHECK();
+                if (int rc = launch_group<true>(split, dim3((unsigned)n_tiles, (unsigned)n_chunks), gsmem, st, b.U, b.tauT,
+                                              b.betaT, b.grp, b.tlo, b.thi, K, (int)S, (int)P, (long long)N,
+                                              (long long)pitch, flexible ? 0 : 1, sb_chunk, b.keys, nullptr)) return rc;
                 beam_direct_kernel<true><<<dgrid, D_THREADS, dsmem, st>>>(
                     b.U, d_tau, d_beta, b.dlist, b.dcount, b.tlo, b.thi, (int)S, (int)P, (long long)N,
                     (long long)pitch, flexible ? 0 : 1, b.keys, nullptr);
@@ -880,20 +1047,10 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
             sb_chunk = (n_sb + 65534) / 65535;
             n_chunks = (n_sb + sb_chunk - 1) / sb_chunk;
         }
-        BPMF_CUDA(cudaFuncSetAttribute(beam_group_kernel<false, 1>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        BPMF_CUDA(cudaFuncSetAttribute(beam_group_kernel<false, 2>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         MainKernelTimer timer(st);
-        dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
-        beam_group_kernel<false, 1><<<grid, F_THREADS, gsmem, st>>>(
-            b.U, b.tauT, b.betaT, b.grp, b.dcount + 1, b.tlo, b.thi, K, (int)S, (int)P, (long long)N, (long long)pitch,
-            flexible ? 0 : 1, sb_chunk, nullptr, d_beam);
-        BPMF_LAUNCH_CHECK();
-        beam_group_kernel<false, 2><<<grid, F_THREADS, gsmem, st>>>(
-            b.U, b.tauT, b.betaT, b.grp, b.dcount + 1, b.tlo, b.thi, K, (int)S, (int)P, (long long)N, (long long)pitch,
-            flexible ? 0 : 1, sb_chunk, nullptr, d_beam);
-        BPMF_LAUNCH_CHECK();
+        if (int rc = launch_group<false>(split, dim3((unsigned)n_tiles, (unsigned)n_chunks), gsmem, st, b.U, b.tauT, b.betaT,
+                                       b.grp, b.tlo, b.thi, K, (int)S, (int)P, (long long)N, (long long)pitch,
+                                       flexible ? 0 : 1, sb_chunk, nullptr, d_beam)) return rc;
         beam_direct_kernel<false><<<dgrid, D_THREADS, dsmem, st>>>(
             b.U, d_tau, d_beta, b.dlist, b.dcount, b.tlo, b.thi, (int)S, (int)P, (long long)N, (long long)pitch,
             flexible ? 0 : 1, nullptr, d_beam);
@@ -920,6 +1077,18 @@ static int beam_run(bool reduce_max, const float *d_features, const int *d_tau, 
 }  // namespace bpmf
 
 using namespace bpmf;
+
+#ifdef BEAM_DIAG
+extern "C" int bpmf_beam_diag(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, bpmf::beam_diag, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(bpmf::beam_diag, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 extern "C" size_t bpmf_beam_workspace_bytes(size_t K, size_t S, size_t C, size_t P, size_t N) {
     (void)C;

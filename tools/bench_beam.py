@@ -190,5 +190,6 @@ if __name__ == "__main__":
     ap.add_argument("--keep", type=int, default=32, help="stations with non-zero source weight per source")
     ap.add_argument("--random-moveouts", action="store_true")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=2)
     a = ap.parse_args()
-    print(json.dumps(run(a.sources, a.samples, a.stations, a.keep, a.random_moveouts, a.steps)))
+    print(json.dumps(run(a.sources, a.samples, a.stations, a.keep, a.random_moveouts, a.steps, a.warmup)))
