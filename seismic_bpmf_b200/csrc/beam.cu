@@ -1126,37 +1126,65 @@ extern "C" int bpmf_beam_merge_dev(float *d_max_a, int *d_arg_a, const float *d_
     return BPMF_OK;
 }
 
+// Host-pointer form (what beampower.beamform calls).  Calls whose device footprint stays under 1 GB run out of the
+// calling thread's grow-only scratch and stream (HostPool: no cudaMalloc / cudaFree per call -- BPMF calls this once
+// per batch of sources or per day); larger ones allocate and free their own buffers so that nothing of that size
+// stays resident between calls.
 static int beam_host(bool reduce_max, const float *features, const int *moveouts, const float *wp,
                      const float *beta, size_t K, size_t S, size_t C, size_t P, size_t N, int flexible,
                      int source_offset, float *maxbeam, int *arg, float *beam) {
-    DevBuf f, tau, dwp, dbeta, ws, o1, o2;
-    BPMF_CUDA(f.alloc(sizeof(float) * S * C * N));
-    BPMF_CUDA(tau.alloc(sizeof(int) * K * S * P));
-    BPMF_CUDA(dwp.alloc(sizeof(float) * S * C * P));
-    BPMF_CUDA(dbeta.alloc(sizeof(float) * K * S));
     const size_t wsb = bpmf_beam_workspace_bytes(K, S, C, P, N);
-    BPMF_CUDA(ws.alloc(wsb));
+    const size_t n_f = S * C * N, n_tau = K * S * P, n_wp = S * C * P, n_beta = K * S;
+    const size_t n_out = reduce_max ? N : K * N;
+    const size_t total = sizeof(float) * (n_f + n_wp + n_beta + n_out) + sizeof(int) * (n_tau + (reduce_max ? N : 0)) + wsb +
+                         8 * 256;
+    DevBuf f, tau, dwp, dbeta, ws, o1, o2;
+    float *d_f, *d_wp, *d_beta, *d_o1;
+    int *d_tau, *d_o2 = nullptr;
+    void *d_ws;
     cudaStream_t st = nullptr;
-    BPMF_CUDA(cudaMemcpyAsync(f.p, features, sizeof(float) * S * C * N, cudaMemcpyHostToDevice, st));
-    BPMF_CUDA(cudaMemcpyAsync(tau.p, moveouts, sizeof(int) * K * S * P, cudaMemcpyHostToDevice, st));
-    BPMF_CUDA(cudaMemcpyAsync(dwp.p, wp, sizeof(float) * S * C * P, cudaMemcpyHostToDevice, st));
-    BPMF_CUDA(cudaMemcpyAsync(dbeta.p, beta, sizeof(float) * K * S, cudaMemcpyHostToDevice, st));
+    if (total <= ((size_t)1 << 30)) {
+        HostPool &pool = host_pool();
+        BPMF_CUDA(pool.begin(total));
+        st = pool.st;
+        d_f = pool.take<float>(n_f);
+        d_tau = pool.take<int>(n_tau);
+        d_wp = pool.take<float>(n_wp);
+        d_beta = pool.take<float>(n_beta);
+        d_o1 = pool.take<float>(n_out);
+        if (reduce_max) d_o2 = pool.take<int>(N);
+        d_ws = pool.take<char>(wsb);
+    } else {
+        BPMF_CUDA(f.alloc(sizeof(float) * n_f));
+        BPMF_CUDA(tau.alloc(sizeof(int) * n_tau));
+        BPMF_CUDA(dwp.alloc(sizeof(float) * n_wp));
+        BPMF_CUDA(dbeta.alloc(sizeof(float) * n_beta));
+        BPMF_CUDA(ws.alloc(wsb));
+        BPMF_CUDA(o1.alloc(sizeof(float) * n_out));
+        if (reduce_max) BPMF_CUDA(o2.alloc(sizeof(int) * N));
+        d_f = f.as<float>();
+        d_tau = tau.as<int>();
+        d_wp = dwp.as<float>();
+        d_beta = dbeta.as<float>();
+        d_o1 = o1.as<float>();
+        d_o2 = o2.as<int>();
+        d_ws = ws.p;
+    }
+    BPMF_CUDA(cudaMemcpyAsync(d_f, features, sizeof(float) * n_f, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(d_tau, moveouts, sizeof(int) * n_tau, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(d_wp, wp, sizeof(float) * n_wp, cudaMemcpyHostToDevice, st));
+    BPMF_CUDA(cudaMemcpyAsync(d_beta, beta, sizeof(float) * n_beta, cudaMemcpyHostToDevice, st));
     int rc;
     if (reduce_max) {
-        BPMF_CUDA(o1.alloc(sizeof(float) * N));
-        BPMF_CUDA(o2.alloc(sizeof(int) * N));
-        rc = bpmf_beamform_max_dev(f.as<float>(), tau.as<int>(), dwp.as<float>(), dbeta.as<float>(), K,
-                                   S, C, P, N, flexible, source_offset, ws.p, wsb, o1.as<float>(),
-                                   o2.as<int>(), st);
+        rc = bpmf_beamform_max_dev(d_f, d_tau, d_wp, d_beta, K, S, C, P, N, flexible, source_offset, d_ws, wsb, d_o1,
+                                   d_o2, st);
         if (rc != BPMF_OK) return rc;
-        BPMF_CUDA(cudaMemcpyAsync(maxbeam, o1.p, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
-        BPMF_CUDA(cudaMemcpyAsync(arg, o2.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+        BPMF_CUDA(cudaMemcpyAsync(maxbeam, d_o1, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+        BPMF_CUDA(cudaMemcpyAsync(arg, d_o2, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
     } else {
-        BPMF_CUDA(o1.alloc(sizeof(float) * K * N));
-        rc = bpmf_beamform_full_dev(f.as<float>(), tau.as<int>(), dwp.as<float>(), dbeta.as<float>(), K,
-                                    S, C, P, N, flexible, ws.p, wsb, o1.as<float>(), st);
+        rc = bpmf_beamform_full_dev(d_f, d_tau, d_wp, d_beta, K, S, C, P, N, flexible, d_ws, wsb, d_o1, st);
         if (rc != BPMF_OK) return rc;
-        BPMF_CUDA(cudaMemcpyAsync(beam, o1.p, sizeof(float) * K * N, cudaMemcpyDeviceToHost, st));
+        BPMF_CUDA(cudaMemcpyAsync(beam, d_o1, sizeof(float) * K * N, cudaMemcpyDeviceToHost, st));
     }
     BPMF_CUDA(cudaStreamSynchronize(st));
     return BPMF_OK;
