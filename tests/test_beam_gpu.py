@@ -139,8 +139,9 @@ def test_unused_station_garbage_is_ignored():
 @pytest.mark.parametrize("K,S,C,P,N", [(37, 40, 3, 3, 2500), (21, 200, 2, 2, 1800), (5, 1, 1, 1, 900)])
 def test_station_counts_beyond_one_warp_and_legacy_fallback(K, S, C, P, N):
     """More (station, phase) rows than lanes (the pack kernel and the producer loop over them), and a network
-    large enough (200 stations x 2 phases) that the grouped kernel's parameter buffers no longer allow two CTAs per
-    SM: the barrier-synchronised kernel takes over.  Same answers either way."""
+    large enough (200 stations x 2 phases) that the grouped kernel's parameter buffers and running-max arrays no
+    longer fit the shared memory of one SM for reduce="max": the barrier-synchronised kernel takes over there, while
+    reduce="none" still runs the grouped kernel.  Same answers either way."""
     f, tau, wp, ws = _synth.beam_case(K, S, C, P, N, seed=K + S, coherent=True, sparse_sources=(S == 40))
     mb, am = bp.beamform(f, tau, wp, ws)
     full = bp.beamform(f, tau, wp, ws, reduce="none")
